@@ -1,0 +1,660 @@
+// Layer program, linearisation and curvature-matrix-vector products for fully connected nets.
+//
+// Replaces, behind the C ABI of include/hf_b200.h, what the reference obtains from BackPACK/autograd:
+//   hf_lin_forward / hf_lin_gradient  <- forward() + autograd.grad, optimizer.py:223, :231-234
+//   hf_ggn_matvec                     <- _Gv,  optimizer.py:457-462  (R-op, loss Hessian, L-op)
+//   hf_hessian_matvec                 <- _Hv,  optimizer.py:450-455  (Pearlmutter R{backprop})
+//   hf_fisher_diag                    <- diag_EF_backpack, preconditioners.py:11-60
+// Activations are computed once per linearisation and stay resident in HBM for the whole solve (the
+// reference re-runs the forward pass for every chunk on every CG iteration, optimizer.py:805-814).
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace hf {
+
+struct Layer {
+  int in, out, act, has_bias;
+  int64_t w_off, b_off;
+  const float* w_frozen;
+  const float* b_frozen;
+};
+
+}  // namespace hf
+
+struct hf_net {
+  std::vector<hf::Layer> L;
+  int loss, reduction;
+  int64_t P;
+  int first_trainable;
+  int max_width;
+  int classes;
+  int engine;  // 0 = SIMT everywhere, 1 = tcgen05 where the shape allows
+};
+
+struct hf_lin {
+  const hf_net* net;
+  int64_t N;
+  int flags;
+  const float* x;
+  std::vector<float*> a;      // a[l]: output of layer l (post-activation); a[L-1] = network output
+  std::vector<float*> delta;  // HESSIAN: dloss/dz_l
+  std::vector<float*> ga;     // HESSIAN: dloss/da_l for layers whose activation has curvature
+  std::vector<float*> ra;     // HESSIAN: R{a_l}
+  std::vector<float*> rz;     // HESSIAN: R{z_l} for layers whose activation has curvature
+  float* prob;                // [N,C] softmax / sigmoid probabilities
+  float* deltaL;              // [N,C] dloss/dz of the last layer
+  float* buf[2];              // ping-pong [N,max_width]
+  float* partial;             // split-K partial tiles
+  size_t partial_floats;
+  double* loss_partial;
+  int loss_blocks;
+  int64_t n_total;
+  bool have_forward, have_gradient;
+};
+
+namespace hf {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline bool curved(int act) { return act == HF_ACT_SIGMOID || act == HF_ACT_TANH; }
+
+// ---- row-wise loss kernels ---------------------------------------------------------------------
+
+struct LossArgs {
+  const float* out;  // [N,C] network outputs (post final activation)
+  const void* target;
+  int64_t N;
+  int C;
+  int loss, final_act;
+  float scale;    // 1/n_total (ce mean), 1/(n_total*C) (mse/bce mean), 1 (sum)
+  float* prob;    // may be null
+  float* delta;   // may be null: dloss/dz_L (through the final activation)
+  double* partial;
+};
+
+// one warp per row; lanes stride over the C outputs
+__global__ void __launch_bounds__(256) loss_forward_kernel(LossArgs a) {
+  __shared__ double sm[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double block_loss = 0.0;
+  for (int64_t n = (int64_t)blockIdx.x * 8 + warp; n < a.N; n += (int64_t)gridDim.x * 8) {
+    const float* z = a.out + n * a.C;
+    float row = 0.f;
+    if (a.loss == HF_LOSS_SOFTMAX_CE) {
+      const int64_t t = static_cast<const int64_t*>(a.target)[n];
+      float mx = -INFINITY;
+      for (int c = lane; c < a.C; c += 32) mx = fmaxf(mx, z[c]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float se = 0.f;
+      for (int c = lane; c < a.C; c += 32) se += expf(z[c] - mx);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      const float lse = mx + logf(se);
+      for (int c = lane; c < a.C; c += 32) {
+        const float p = expf(z[c] - lse);
+        if (a.prob) a.prob[n * a.C + c] = p;
+        if (a.delta) a.delta[n * a.C + c] = a.scale * (p - (c == t ? 1.f : 0.f));
+      }
+      row = (t >= 0 && t < a.C) ? (lse - z[t]) : 0.f;  // every lane holds the same value
+    } else {
+      const float* t = static_cast<const float*>(a.target) + n * a.C;
+      float acc = 0.f;
+      for (int c = lane; c < a.C; c += 32) {
+        const float zc = z[c], tc = t[c];
+        float d;
+        if (a.loss == HF_LOSS_MSE) {
+          const float e = zc - tc;
+          acc += e * e;
+          d = 2.f * e;
+        } else {  // sigmoid + binary cross entropy on logits
+          const float p = 1.f / (1.f + expf(-zc));
+          acc += fmaxf(zc, 0.f) - zc * tc + log1pf(expf(-fabsf(zc)));
+          d = p - tc;
+          if (a.prob) a.prob[n * a.C + c] = p;
+        }
+        if (a.delta) a.delta[n * a.C + c] = a.scale * d * act_d1(a.final_act, zc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      row = acc;
+    }
+    block_loss += (double)row;
+  }
+  if (lane == 0) sm[warp] = block_loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    a.partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ partial, int n, double scale, double* acc) {
+  __shared__ double scratch[4 * 33];
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v[0] += partial[i];
+  block_sum<1>(v, scratch);
+  if (threadIdx.x == 0) *acc += scale * v[0];
+}
+
+// u = H_loss * Rz, row-wise, in place (then through the final activation's derivative):
+//   mse: 2*scale*Rz     softmax-ce: scale*(p.Rz - p (p^T Rz))     sigmoid-bce: scale*p(1-p)*Rz
+struct HessArgs {
+  float* rz;  // [N,C] in: R{output}, out: u
+  const float* prob;
+  const float* out;
+  int64_t N;
+  int C;
+  int loss, final_act;
+  float scale;
+  const int32_t* skip;
+};
+
+__global__ void __launch_bounds__(256) loss_hessian_kernel(HessArgs a) {
+  if (a.skip && *a.skip) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t n = (int64_t)blockIdx.x * 8 + warp; n < a.N; n += (int64_t)gridDim.x * 8) {
+    float* r = a.rz + n * a.C;
+    if (a.loss == HF_LOSS_SOFTMAX_CE) {
+      const float* p = a.prob + n * a.C;
+      float dot = 0.f;
+      for (int c = lane; c < a.C; c += 32) dot += p[c] * r[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      for (int c = lane; c < a.C; c += 32) r[c] = a.scale * p[c] * (r[c] - dot);
+    } else if (a.loss == HF_LOSS_MSE) {
+      for (int c = lane; c < a.C; c += 32) {
+        float v = 2.f * a.scale * r[c];
+        if (a.final_act != HF_ACT_NONE) v *= act_d1(a.final_act, a.out[n * a.C + c]);
+        r[c] = v;
+      }
+    } else {
+      const float* p = a.prob + n * a.C;
+      for (int c = lane; c < a.C; c += 32) r[c] = a.scale * p[c] * (1.f - p[c]) * r[c];
+    }
+  }
+}
+
+// ---- helpers -----------------------------------------------------------------------------------
+
+static inline const float* weight_ptr(const Layer& l, const float* theta) {
+  return l.w_off >= 0 ? theta + l.w_off : l.w_frozen;
+}
+static inline const float* bias_ptr(const Layer& l, const float* theta) {
+  if (!l.has_bias) return nullptr;
+  return l.b_off >= 0 ? theta + l.b_off : l.b_frozen;
+}
+
+struct SplitPlan {
+  int splits;
+  int k_per_split;
+};
+
+// split the batch dimension of a weight-gradient contraction so the grid fills the machine
+static SplitPlan plan_split(int M, int N, int64_t K) {
+  const TileChoice t = choose_tile(M, N);
+  const int64_t tiles = (int64_t)((M + t.bm - 1) / t.bm) * ((N + t.bn - 1) / t.bn);
+  const int64_t ktiles = (K + kBK - 1) / kBK;
+  int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+  int64_t max_split = ktiles / 8;  // at least 8 k-tiles (128 samples) per split
+  if (max_split < 1) max_split = 1;
+  if (want > max_split) want = max_split;
+  if (want > 64) want = 64;
+  if (want < 1) want = 1;
+  const int64_t kt_per = (ktiles + want - 1) / want;
+  SplitPlan p;
+  p.k_per_split = (int)(kt_per * kBK);
+  p.splits = (int)((ktiles + kt_per - 1) / kt_per);
+  return p;
+}
+
+static int colsum_plan(int64_t rows) {
+  int64_t s = (rows + 511) / 512;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+static Operand op_kc(const float* p, int64_t ld) { return Operand{p, ld, 1}; }   // [MN,K], K contiguous
+static Operand op_mnc(const float* p, int64_t ld) { return Operand{p, 1, ld}; }  // [K,MN], MN contiguous
+
+static GemmArgs blank_gemm() {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.alpha = 1.f;
+  g.split_k = 1;
+  return g;
+}
+
+// dispatch one contraction to the tensor-core engine when the net asks for it and the shape fits
+static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream) {
+  if (net->engine == 1 && tc_supported(g)) return launch_gemm_tc(g, stream);
+  return launch_gemm_simt(g, stream);
+}
+
+// weight gradient (or its Fisher square): out[out,in] (+)= scale * sum_pairs A_s^T B_s over the batch
+static int weight_contraction(hf_lin* lin, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
+                              float* out, float scale, int accumulate, const int32_t* skip, cudaStream_t stream) {
+  const SplitPlan sp = plan_split(M, N, lin->N);
+  HF_REQUIRE((size_t)sp.splits * M * N <= lin->partial_floats, HF_ERR_WORKSPACE, "split-K scratch too small");
+  GemmArgs g = blank_gemm();
+  g.M = M, g.N = N, g.K = (int)lin->N, g.n_pairs = n_pairs;
+  for (int s = 0; s < n_pairs; ++s) g.A[s] = A[s], g.B[s] = B[s];
+  g.square = square;
+  g.C = lin->partial, g.ldc = N;
+  g.epi = EPI_STORE;
+  g.split_k = sp.splits, g.k_per_split = sp.k_per_split;
+  g.skip = skip;
+  int rc = run_gemm(lin->net, g, stream);
+  if (rc) return rc;
+  const int64_t count = (int64_t)M * N;
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, sp.splits, count, count, out, scale,
+                                                              accumulate, skip);
+  HF_CUDA(cudaGetLastError());
+  return HF_OK;
+}
+
+static int bias_contraction(hf_lin* lin, const float* d, int cols, int square, float* out, float scale, int accumulate,
+                            const int32_t* skip, cudaStream_t stream) {
+  const int splits = colsum_plan(lin->N);
+  const int rows_per = (int)((lin->N + splits - 1) / splits);
+  HF_REQUIRE((size_t)splits * cols <= lin->partial_floats, HF_ERR_WORKSPACE, "column-sum scratch too small");
+  colsum_kernel<<<dim3((cols + 31) / 32, splits), dim3(32, 8), 0, stream>>>(d, lin->N, cols, cols, rows_per, square,
+                                                                            lin->partial, skip);
+  HF_CUDA(cudaGetLastError());
+  reduce_partials_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(lin->partial, splits, cols, cols, out, scale,
+                                                                accumulate, skip);
+  HF_CUDA(cudaGetLastError());
+  return HF_OK;
+}
+
+static float loss_scale(const hf_net* net, int64_t n_total) {
+  if (net->reduction == HF_RED_SUM) return 1.f;
+  if (net->loss == HF_LOSS_SOFTMAX_CE) return (float)(1.0 / (double)n_total);
+  return (float)(1.0 / ((double)n_total * (double)net->classes));
+}
+
+// R-op forward: R{output} = J v into lin->buf[which]; returns the buffer index holding it
+static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hessian, const int32_t* skip,
+                       cudaStream_t stream, int* out_buf) {
+  const hf_net* net = lin->net;
+  const int nl = (int)net->L.size();
+  const float* cur = nullptr;
+  int which = 0;
+  for (int l = net->first_trainable; l < nl; ++l) {
+    const Layer& L = net->L[l];
+    const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
+    GemmArgs g = blank_gemm();
+    g.M = (int)lin->N, g.N = L.out, g.K = L.in;
+    int np = 0;
+    if (L.w_off >= 0) {
+      g.A[np] = op_kc(a_in, L.in), g.B[np] = op_kc(v + L.w_off, L.in);
+      ++np;
+    }
+    if (cur) {
+      g.A[np] = op_kc(cur, L.in), g.B[np] = op_kc(weight_ptr(L, theta), L.in);
+      ++np;
+    }
+    float* dst = (hessian && l < nl - 1) ? lin->ra[l] : lin->buf[which];
+    if (np == 0) {
+      // a frozen layer fed by a zero tangent contributes only its (frozen) nothing: R{z} = 0
+      HF_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * lin->N * L.out, stream));
+    } else {
+      g.n_pairs = np;
+      g.C = dst, g.ldc = L.out;
+      g.epi = EPI_BIAS_DACT, g.act = L.act;
+      g.bias = (L.has_bias && L.b_off >= 0) ? v + L.b_off : nullptr;
+      g.aux = lin->a[l], g.ldaux = L.out;
+      g.C2 = (hessian && curved(L.act)) ? lin->rz[l] : nullptr;
+      g.skip = skip;
+      int rc = run_gemm(net, g, stream);
+      if (rc) return rc;
+    }
+    cur = dst;
+    if (!(hessian && l < nl - 1)) which ^= 1;
+  }
+  // cur is the last layer's output tangent and lives in a ping-pong buffer
+  *out_buf = (cur == lin->buf[0]) ? 0 : 1;
+  return HF_OK;
+}
+
+static int apply_loss_hessian(hf_lin* lin, float* rz, const int32_t* skip, cudaStream_t stream) {
+  const hf_net* net = lin->net;
+  HessArgs h;
+  h.rz = rz, h.prob = lin->prob, h.out = lin->a.back();
+  h.N = lin->N, h.C = net->classes, h.loss = net->loss, h.final_act = net->L.back().act;
+  h.scale = loss_scale(net, lin->n_total);
+  h.skip = skip;
+  int64_t blocks = (lin->N + 7) / 8;
+  if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+  loss_hessian_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h);
+  HF_CUDA(cudaGetLastError());
+  return HF_OK;
+}
+
+enum BackMode { BACK_GRADIENT, BACK_GGN, BACK_FISHER, BACK_HESSIAN };
+
+// Transposed sweep from the output signal `top` ([N,C]) down to the first trainable layer.
+//   GRADIENT: out (+)= J^T top; with HF_LIN_HESSIAN also stores delta_l and dL/da_l
+//   GGN:      out (+)= J^T top
+//   FISHER:   out (+)= scale * sum_n (per-sample gradient)^2
+//   HESSIAN:  top = R{delta_L}; adds the delta_l^T R{a_{l-1}} and delta_l V_l terms and the act'' term
+static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const float* top, int top_buf, float* out,
+                          int accumulate, BackMode mode, const int32_t* skip, cudaStream_t stream) {
+  const hf_net* net = lin->net;
+  const int nl = (int)net->L.size();
+  const bool keep = mode == BACK_GRADIENT && (lin->flags & HF_LIN_HESSIAN);
+  const int square = mode == BACK_FISHER;
+  float scale = 1.f;
+  if (mode == BACK_FISHER && net->reduction == HF_RED_MEAN) scale = (float)lin->n_total;
+  const float* cur = top;
+  int which = top_buf >= 0 ? (top_buf ^ 1) : 0;  // next free ping-pong buffer
+  for (int l = nl - 1; l >= net->first_trainable; --l) {
+    const Layer& L = net->L[l];
+    const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
+    if (L.w_off >= 0) {
+      Operand A[2], B[2];
+      int np = 0;
+      A[np] = op_mnc(cur, L.out), B[np] = op_mnc(a_in, L.in), ++np;
+      if (mode == BACK_HESSIAN && l > net->first_trainable) {
+        A[np] = op_mnc(lin->delta[l], L.out), B[np] = op_mnc(lin->ra[l - 1], L.in), ++np;
+      }
+      int rc = weight_contraction(lin, L.out, L.in, np, A, B, square, out + L.w_off, scale, accumulate, skip, stream);
+      if (rc) return rc;
+    }
+    if (L.has_bias && L.b_off >= 0) {
+      int rc = bias_contraction(lin, cur, L.out, square, out + L.b_off, scale, accumulate, skip, stream);
+      if (rc) return rc;
+    }
+    if (l > net->first_trainable) {
+      const Layer& Lp = net->L[l - 1];
+      GemmArgs g = blank_gemm();
+      g.M = (int)lin->N, g.N = L.in, g.K = L.out;
+      int np = 0;
+      g.A[np] = op_kc(cur, L.out), g.B[np] = op_mnc(weight_ptr(L, theta), L.in), ++np;
+      if (mode == BACK_HESSIAN && L.w_off >= 0) {
+        g.A[np] = op_kc(lin->delta[l], L.out), g.B[np] = op_mnc(v + L.w_off, L.in), ++np;
+      }
+      g.n_pairs = np;
+      float* dst = keep ? lin->delta[l - 1] : lin->buf[which];
+      g.C = dst, g.ldc = L.in;
+      g.act = Lp.act;
+      g.aux = lin->a[l - 1], g.ldaux = L.in;
+      if (mode == BACK_HESSIAN) {
+        g.epi = EPI_DACT_H;
+        if (curved(Lp.act)) g.h_ga = lin->ga[l - 1], g.h_rz = lin->rz[l - 1];
+      } else {
+        g.epi = EPI_DACT;
+        g.C2 = (keep && curved(Lp.act)) ? lin->ga[l - 1] : nullptr;
+      }
+      g.skip = skip;
+      int rc = run_gemm(net, g, stream);
+      if (rc) return rc;
+      cur = dst;
+      if (!keep) which ^= 1;
+    }
+  }
+  return HF_OK;
+}
+
+}  // namespace hf
+
+using namespace hf;
+
+extern "C" {
+
+int hf_net_create(const hf_layer_desc* layers, int32_t n_layers, int32_t loss, int32_t reduction, int64_t n_params,
+                  hf_net_t** out) {
+  HF_REQUIRE(layers && out && n_layers >= 1, HF_ERR_INVALID, "hf_net_create: need at least one layer");
+  HF_REQUIRE(loss >= HF_LOSS_MSE && loss <= HF_LOSS_SIGMOID_BCE, HF_ERR_INVALID, "hf_net_create: unknown loss %d", loss);
+  HF_REQUIRE(reduction == HF_RED_MEAN || reduction == HF_RED_SUM, HF_ERR_INVALID, "hf_net_create: unknown reduction");
+  hf_net* net = new (std::nothrow) hf_net();
+  HF_REQUIRE(net, HF_ERR_INVALID, "hf_net_create: out of host memory");
+  net->loss = loss, net->reduction = reduction, net->P = n_params;
+  net->first_trainable = -1, net->max_width = 0, net->engine = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    const hf_layer_desc& d = layers[i];
+    bool ok = d.in_features > 0 && d.out_features > 0 && d.act >= HF_ACT_NONE && d.act <= HF_ACT_TANH;
+    ok = ok && (i == 0 || d.in_features == layers[i - 1].out_features);
+    ok = ok && (d.w_offset >= 0 ? d.w_offset + (int64_t)d.in_features * d.out_features <= n_params : d.d_w_frozen != nullptr);
+    if (d.has_bias) ok = ok && (d.b_offset >= 0 ? d.b_offset + d.out_features <= n_params : d.d_b_frozen != nullptr);
+    if (!ok) {
+      delete net;
+      HF_REQUIRE(false, HF_ERR_INVALID, "hf_net_create: layer %d is inconsistent", i);
+    }
+    Layer l{d.in_features, d.out_features, d.act, d.has_bias, d.w_offset, d.has_bias ? d.b_offset : -1, d.d_w_frozen,
+            d.d_b_frozen};
+    if (net->first_trainable < 0 && (l.w_off >= 0 || l.b_off >= 0)) net->first_trainable = i;
+    net->max_width = std::max(net->max_width, std::max(l.in, l.out));
+    net->L.push_back(l);
+  }
+  net->classes = net->L.back().out;
+  if (net->first_trainable < 0) {
+    delete net;
+    HF_REQUIRE(false, HF_ERR_INVALID, "hf_net_create: no trainable parameter");
+  }
+  if (net->L.back().act != HF_ACT_NONE && loss != HF_LOSS_MSE) {
+    delete net;
+    HF_REQUIRE(false, HF_ERR_UNSUPPORTED, "hf_net_create: softmax-ce / sigmoid-bce expect raw logits from the last layer");
+  }
+  *out = net;
+  return HF_OK;
+}
+
+void hf_net_destroy(hf_net_t* net) { delete net; }
+
+int hf_net_set_engine(hf_net_t* net, int32_t engine) {
+  HF_REQUIRE(net && (engine == 0 || engine == 1), HF_ERR_INVALID, "hf_net_set_engine: engine must be 0 or 1");
+  net->engine = engine;
+  return HF_OK;
+}
+
+// one pass over the carve-up: either measures (base == nullptr) or assigns pointers
+static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin* lin) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> char* {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int nl = (int)net->L.size();
+  const bool hess = flags & HF_LIN_HESSIAN, loss_only = flags & HF_LIN_LOSS_ONLY;
+  if (lin) lin->a.assign(nl, nullptr), lin->delta.assign(nl, nullptr), lin->ga.assign(nl, nullptr),
+      lin->ra.assign(nl, nullptr), lin->rz.assign(nl, nullptr);
+  if (loss_only) {
+    // activations are not kept: alternate between two buffers
+    float* b0 = (float*)take(sizeof(float) * N * net->max_width);
+    float* b1 = (float*)take(sizeof(float) * N * net->max_width);
+    if (lin)
+      for (int l = 0; l < nl; ++l) lin->a[l] = (l & 1) ? b1 : b0;
+  } else {
+    for (int l = 0; l < nl; ++l) {
+      float* p = (float*)take(sizeof(float) * N * net->L[l].out);
+      if (lin) lin->a[l] = p;
+    }
+  }
+  float* prob = nullptr;
+  float* dL = nullptr;
+  if (!loss_only) {
+    if (net->loss != HF_LOSS_MSE) prob = (float*)take(sizeof(float) * N * net->classes);
+    dL = (float*)take(sizeof(float) * N * net->classes);
+  }
+  float* b0 = loss_only ? nullptr : (float*)take(sizeof(float) * N * net->max_width);
+  float* b1 = loss_only ? nullptr : (float*)take(sizeof(float) * N * net->max_width);
+  // split-K scratch: the largest weight-gradient partial set, the widest column sum
+  size_t pf = 0;
+  if (!loss_only)
+    for (int l = net->first_trainable; l < nl; ++l) {
+      const Layer& L = net->L[l];
+      if (L.w_off >= 0) pf = std::max(pf, (size_t)plan_split(L.out, L.in, N).splits * L.out * L.in);
+      pf = std::max(pf, (size_t)colsum_plan(N) * L.out);
+    }
+  float* part = pf ? (float*)take(sizeof(float) * pf) : nullptr;
+  int64_t lb = (N + 7) / 8;
+  if (lb > 1024) lb = 1024;
+  double* lp = (double*)take(sizeof(double) * lb);
+  if (hess && !loss_only) {
+    for (int l = net->first_trainable; l < nl; ++l) {
+      const size_t bytes = sizeof(float) * N * net->L[l].out;
+      float* d = (l < nl - 1) ? (float*)take(bytes) : nullptr;  // the last layer's delta is deltaL
+      float* r = (l < nl - 1) ? (float*)take(bytes) : nullptr;
+      float* g = nullptr;
+      float* z = nullptr;
+      if (l < nl - 1 && curved(net->L[l].act)) g = (float*)take(bytes), z = (float*)take(bytes);
+      if (lin) lin->delta[l] = d ? d : dL, lin->ra[l] = r, lin->ga[l] = g, lin->rz[l] = z;
+    }
+  }
+  if (lin) {
+    lin->prob = prob, lin->deltaL = dL, lin->buf[0] = b0, lin->buf[1] = b1;
+    lin->partial = part, lin->partial_floats = pf, lin->loss_partial = lp, lin->loss_blocks = (int)lb;
+  }
+  return off;
+}
+
+size_t hf_lin_workspace_bytes(const hf_net_t* net, int64_t batch, int32_t flags) {
+  if (!net || batch <= 0) return 0;
+  return carve(net, batch, flags, nullptr, nullptr);
+}
+
+int hf_lin_create(const hf_net_t* net, int64_t batch, int32_t flags, void* d_workspace, size_t workspace_bytes,
+                  hf_lin_t** out) {
+  HF_REQUIRE(net && out && batch > 0 && d_workspace, HF_ERR_INVALID, "hf_lin_create: bad arguments");
+  HF_REQUIRE(batch < (1ll << 31), HF_ERR_UNSUPPORTED, "hf_lin_create: chunk of %lld samples is too large", (long long)batch);
+  HF_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255u) == 0, HF_ERR_WORKSPACE, "hf_lin_create: workspace must be 256-byte aligned");
+  if ((flags & HF_LIN_HESSIAN) && net->L.back().act != HF_ACT_NONE)
+    HF_REQUIRE(false, HF_ERR_UNSUPPORTED, "Hessian products with an activation after the last layer are not supported");
+  const size_t need = carve(net, batch, flags, nullptr, nullptr);
+  HF_REQUIRE(workspace_bytes >= need, HF_ERR_WORKSPACE, "hf_lin_create: workspace has %zu bytes, need %zu", workspace_bytes, need);
+  hf_lin* lin = new (std::nothrow) hf_lin();
+  HF_REQUIRE(lin, HF_ERR_INVALID, "hf_lin_create: out of host memory");
+  lin->net = net, lin->N = batch, lin->flags = flags, lin->x = nullptr, lin->n_total = batch;
+  lin->have_forward = lin->have_gradient = false;
+  carve(net, batch, flags, static_cast<char*>(d_workspace), lin);
+  *out = lin;
+  return HF_OK;
+}
+
+void hf_lin_destroy(hf_lin_t* lin) { delete lin; }
+
+const float* hf_lin_logits(const hf_lin_t* lin) { return lin ? lin->a.back() : nullptr; }
+
+int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const void* d_targets, int64_t n_total,
+                   double* d_loss_acc, void* stream_) {
+  HF_REQUIRE(lin && d_x && d_targets && n_total > 0, HF_ERR_INVALID, "hf_lin_forward: bad arguments");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const hf_net* net = lin->net;
+  HF_REQUIRE(d_theta || net->P == 0, HF_ERR_INVALID, "hf_lin_forward: theta is null");
+  const int nl = (int)net->L.size();
+  lin->x = d_x, lin->n_total = n_total;
+  for (int l = 0; l < nl; ++l) {
+    const Layer& L = net->L[l];
+    GemmArgs g = blank_gemm();
+    g.M = (int)lin->N, g.N = L.out, g.K = L.in, g.n_pairs = 1;
+    g.A[0] = op_kc(l == 0 ? d_x : lin->a[l - 1], L.in);
+    g.B[0] = op_kc(weight_ptr(L, d_theta), L.in);
+    g.C = lin->a[l], g.ldc = L.out;
+    g.epi = EPI_BIAS_ACT, g.act = L.act, g.bias = bias_ptr(L, d_theta);
+    int rc = run_gemm(net, g, stream);
+    if (rc) return rc;
+  }
+  LossArgs a;
+  a.out = lin->a.back(), a.target = d_targets, a.N = lin->N, a.C = net->classes;
+  a.loss = net->loss, a.final_act = net->L.back().act;
+  a.scale = loss_scale(net, n_total);
+  a.prob = lin->prob, a.delta = lin->deltaL, a.partial = lin->loss_partial;
+  int64_t blocks = (lin->N + 7) / 8;
+  if (blocks > lin->loss_blocks) blocks = lin->loss_blocks;
+  loss_forward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  HF_CUDA(cudaGetLastError());
+  if (d_loss_acc) {
+    loss_finalize_kernel<<<1, 256, 0, stream>>>(lin->loss_partial, (int)blocks, (double)a.scale, d_loss_acc);
+    HF_CUDA(cudaGetLastError());
+  }
+  lin->have_forward = true, lin->have_gradient = false;
+  return HF_OK;
+}
+
+static int check_ready(const hf_lin* lin, const char* who, bool need_grad) {
+  HF_REQUIRE(lin, HF_ERR_INVALID, "%s: null linearisation", who);
+  HF_REQUIRE(!(lin->flags & HF_LIN_LOSS_ONLY), HF_ERR_INVALID, "%s: linearisation was created loss-only", who);
+  HF_REQUIRE(lin->have_forward, HF_ERR_INVALID, "%s: call hf_lin_forward first", who);
+  HF_REQUIRE(!need_grad || lin->have_gradient, HF_ERR_INVALID, "%s: call hf_lin_gradient first", who);
+  return HF_OK;
+}
+
+int hf_lin_gradient(hf_lin_t* lin, const float* d_theta, float* d_grad, int32_t accumulate, void* stream) {
+  int rc = check_ready(lin, "hf_lin_gradient", false);
+  if (rc) return rc;
+  HF_REQUIRE(d_grad, HF_ERR_INVALID, "hf_lin_gradient: null output");
+  rc = backward_sweep(lin, d_theta, nullptr, lin->deltaL, -1, d_grad, accumulate, BACK_GRADIENT, nullptr,
+                      (cudaStream_t)stream);
+  if (rc == HF_OK) lin->have_gradient = true;
+  return rc;
+}
+
+int hf_ggn_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* d_out, int32_t accumulate,
+                  const int32_t* d_skip, void* stream_) {
+  int rc = check_ready(lin, "hf_ggn_matvec", false);
+  if (rc) return rc;
+  HF_REQUIRE(d_v && d_out, HF_ERR_INVALID, "hf_ggn_matvec: null vector");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int top = 0;
+  rc = rop_forward(lin, d_theta, d_v, false, d_skip, stream, &top);
+  if (rc) return rc;
+  rc = apply_loss_hessian(lin, lin->buf[top], d_skip, stream);
+  if (rc) return rc;
+  return backward_sweep(lin, d_theta, d_v, lin->buf[top], top, d_out, accumulate, BACK_GGN, d_skip, stream);
+}
+
+int hf_hessian_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* d_out, int32_t accumulate,
+                      const int32_t* d_skip, void* stream_) {
+  int rc = check_ready(lin, "hf_hessian_matvec", true);
+  if (rc) return rc;
+  HF_REQUIRE(lin->flags & HF_LIN_HESSIAN, HF_ERR_INVALID, "hf_hessian_matvec: linearisation lacks HF_LIN_HESSIAN");
+  HF_REQUIRE(d_v && d_out, HF_ERR_INVALID, "hf_hessian_matvec: null vector");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int top = 0;
+  rc = rop_forward(lin, d_theta, d_v, true, d_skip, stream, &top);
+  if (rc) return rc;
+  rc = apply_loss_hessian(lin, lin->buf[top], d_skip, stream);
+  if (rc) return rc;
+  return backward_sweep(lin, d_theta, d_v, lin->buf[top], top, d_out, accumulate, BACK_HESSIAN, d_skip, stream);
+}
+
+int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t accumulate, void* stream) {
+  int rc = check_ready(lin, "hf_fisher_diag", false);
+  if (rc) return rc;
+  HF_REQUIRE(d_out, HF_ERR_INVALID, "hf_fisher_diag: null output");
+  return backward_sweep(lin, d_theta, nullptr, lin->deltaL, -1, d_out, accumulate, BACK_FISHER, nullptr,
+                        (cudaStream_t)stream);
+}
+
+int hf_contract(int32_t engine, int64_t M, int64_t N, int64_t K, int32_t n_pairs, const hf_operand* A,
+                const hf_operand* B, float* d_C, int64_t ldc, void* d_workspace, size_t workspace_bytes, void* stream) {
+  HF_REQUIRE(A && B && d_C && n_pairs >= 1 && n_pairs <= 2, HF_ERR_INVALID, "hf_contract: bad arguments");
+  HF_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), HF_ERR_INVALID, "hf_contract: bad shape");
+  (void)d_workspace, (void)workspace_bytes;
+  GemmArgs g = blank_gemm();
+  g.M = (int)M, g.N = (int)N, g.K = (int)K, g.n_pairs = n_pairs;
+  for (int s = 0; s < n_pairs; ++s) {
+    g.A[s] = Operand{A[s].d_ptr, A[s].stride_mn, A[s].stride_k};
+    g.B[s] = Operand{B[s].d_ptr, B[s].stride_mn, B[s].stride_k};
+  }
+  g.C = d_C, g.ldc = ldc, g.epi = EPI_STORE;
+  if (engine == 1) {
+    HF_REQUIRE(tc_supported(g), HF_ERR_UNSUPPORTED, "hf_contract: shape/alignment not supported by the tcgen05 engine");
+    return launch_gemm_tc(g, (cudaStream_t)stream);
+  }
+  HF_REQUIRE(engine == 0, HF_ERR_INVALID, "hf_contract: unknown engine %d", engine);
+  return launch_gemm_simt(g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

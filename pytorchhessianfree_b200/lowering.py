@@ -1,0 +1,227 @@
+"""Lower a PyTorch model + loss to the layer program the sm_100a kernels execute.
+
+Two front ends, one result (:class:`Program`):
+
+* :func:`lower_module` for the entry points that receive the model explicitly
+  (``acc_step``, ``get_preconditioner``, ``test_reduction``; reference
+  ``optimizer.py:519-529, 817, 928-937``);
+* :func:`lower_graph` for ``step(forward)``, which only receives an opaque closure
+  (``optimizer.py:137-151``): the structure is recovered from the autograd graph hanging off
+  ``loss`` -- exactly the object the reference hands to BackPACK (``optimizer.py:241-247``).
+
+Anything that cannot be lowered raises ``NotImplementedError`` naming the offending op.  There is no
+autograd or CPU fallback inside this package; a caller with an exotic model can still pass its own
+``mvp`` to ``step`` (``optimizer.py:160-164``), and the solver around it stays native.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from .native import LayerSpec
+
+_ACT_MODULES = {nn.ReLU: "relu", nn.Sigmoid: "sigmoid", nn.Tanh: "tanh"}
+_ACT_NODES = {"ReluBackward0": "relu", "SigmoidBackward0": "sigmoid", "TanhBackward0": "tanh"}
+_REDUCTION_ENUM = {1: "mean", 2: "sum"}  # at::Reduction
+
+
+@dataclass
+class Program:
+    layers: List[LayerSpec]
+    loss: str
+    reduction: str
+    n_params: int
+    inputs: Optional[torch.Tensor] = None   # graph front end only: the constant feeding the first lowered layer
+    targets: Optional[torch.Tensor] = None
+    param_slices: Dict[int, int] = field(default_factory=dict)
+
+
+def flat_offsets(params_list):
+    """id(param) -> offset in the flat trainable vector (reference ``optimizer.py:122`` order)."""
+    table, off = {}, 0
+    for p in params_list:
+        table[id(p)] = off
+        off += p.numel()
+    return table, off
+
+
+def _unsupported(what):
+    raise NotImplementedError(
+        f"{what} cannot be lowered to the sm_100a layer program (supported: Linear, ReLU, Sigmoid, Tanh, Flatten, "
+        "Identity, eval-mode Dropout; MSELoss, CrossEntropyLoss, BCEWithLogitsLoss). Pass your own `mvp` to "
+        "`step`, or restructure the model."
+    )
+
+
+def lower_loss(loss_func):
+    """(kind, reduction) of a supported loss module."""
+    if isinstance(loss_func, nn.MSELoss):
+        kind = "mse"
+    elif isinstance(loss_func, nn.CrossEntropyLoss):
+        if loss_func.weight is not None or loss_func.label_smoothing != 0.0:
+            _unsupported("CrossEntropyLoss with class weights or label smoothing")
+        kind = "ce"
+    elif isinstance(loss_func, nn.BCEWithLogitsLoss):
+        if loss_func.weight is not None or loss_func.pos_weight is not None:
+            _unsupported("BCEWithLogitsLoss with weights")
+        kind = "bce"
+    else:
+        _unsupported(f"loss {type(loss_func).__name__}")
+    if loss_func.reduction not in ("mean", "sum"):
+        _unsupported(f"loss reduction {loss_func.reduction!r}")
+    return kind, loss_func.reduction
+
+
+def _leaves(module):
+    kids = list(module.children())
+    if not kids:
+        yield module
+    else:
+        if not isinstance(module, nn.Sequential):
+            _unsupported(f"container {type(module).__name__} (only nn.Sequential nesting is walked)")
+        for k in kids:
+            yield from _leaves(k)
+
+
+def lower_module(model, loss_func, params_list):
+    """Walk a (nested) ``nn.Sequential`` of Linear/activation layers."""
+    offsets, n_params = flat_offsets(params_list)
+    kind, reduction = lower_loss(loss_func)
+    layers: List[LayerSpec] = []
+    for m in _leaves(model):
+        if isinstance(m, nn.Linear):
+            w, b = m.weight, m.bias
+            spec = LayerSpec(m.in_features, m.out_features, "none", b is not None)
+            for prm, off_name, frozen_name in ((w, "w_offset", "w_frozen"), (b, "b_offset", "b_frozen")):
+                if prm is None:
+                    continue
+                if prm.requires_grad:
+                    if id(prm) not in offsets:
+                        raise ValueError("a trainable model parameter is not among the optimizer's parameters")
+                    setattr(spec, off_name, offsets[id(prm)])
+                else:
+                    setattr(spec, frozen_name, prm.detach())
+            layers.append(spec)
+        elif type(m) in _ACT_MODULES:
+            if not layers or layers[-1].act != "none":
+                _unsupported("an activation that does not directly follow a Linear layer")
+            layers[-1].act = _ACT_MODULES[type(m)]
+        elif isinstance(m, (nn.Identity, nn.Flatten)):
+            if isinstance(m, nn.Flatten) and layers:
+                _unsupported("Flatten after the first Linear layer")
+        elif isinstance(m, nn.Dropout):
+            if m.training and m.p > 0:
+                _unsupported("train-mode Dropout (non-deterministic curvature products)")
+        else:
+            _unsupported(f"module {type(m).__name__}")
+    if not layers:
+        _unsupported("a model without Linear layers")
+    used = {l.w_offset for l in layers if l.w_offset >= 0} | {l.b_offset for l in layers if l.has_bias and l.b_offset >= 0}
+    if used != set(offsets.values()):
+        raise ValueError("the optimizer holds trainable parameters that the model does not use")
+    return Program(layers, kind, reduction, n_params)
+
+
+# ---------------------------------------------------------------------------------------------------
+# autograd-graph front end
+# ---------------------------------------------------------------------------------------------------
+
+def _name(fn):
+    return type(fn).__name__
+
+
+def _leaf_param(fn):
+    """The parameter behind an AccumulateGrad node (through an optional transpose)."""
+    if fn is None:
+        return None
+    if _name(fn) == "TBackward0":
+        fn = fn.next_functions[0][0]
+        if fn is None:
+            return None
+    if _name(fn) != "AccumulateGrad":
+        _unsupported(f"a weight produced by {_name(fn)}")
+    return fn.variable
+
+
+def lower_graph(loss, outputs, params_list):
+    """Recover the layer program from ``loss.grad_fn`` (GGN needs ``outputs``; pass None for Hessian)."""
+    offsets, n_params = flat_offsets(params_list)
+    fn = loss.grad_fn
+    if fn is None:
+        raise ValueError("`forward` returned a loss that does not depend on the parameters")
+    name = _name(fn)
+    if name == "MseLossBackward0":
+        kind, targets, top = "mse", fn._saved_target, fn.next_functions[0][0]
+        out_val = fn._saved_self
+    elif name == "BinaryCrossEntropyWithLogitsBackward0":
+        if fn._saved_weight is not None or fn._saved_pos_weight is not None:
+            _unsupported("binary_cross_entropy_with_logits with weights")
+        kind, targets, top = "bce", fn._saved_target, fn.next_functions[0][0]
+        out_val = fn._saved_self
+    elif name == "NllLossBackward0":
+        if fn._saved_weight is not None:
+            _unsupported("nll_loss with class weights")
+        ls = fn.next_functions[0][0]
+        if ls is None or _name(ls) != "LogSoftmaxBackward0" or ls._saved_dim not in (1, -1):
+            _unsupported("nll_loss that is not fed by log_softmax over the class dimension")
+        kind, targets, top = "ce", fn._saved_target, ls.next_functions[0][0]
+        out_val = None
+        if (targets == fn._saved_ignore_index).any():
+            _unsupported("cross-entropy targets equal to ignore_index")
+    else:
+        _unsupported(f"loss node {name}")
+    reduction = _REDUCTION_ENUM.get(int(fn._saved_reduction))
+    if reduction is None:
+        _unsupported("loss reduction 'none'")
+    if outputs is not None and top is not outputs.grad_fn:
+        _unsupported("a loss that is not applied directly to the `outputs` returned by `forward`")
+
+    # walk down the chain: [act] <- linear <- [act] <- linear ...
+    rev: List[LayerSpec] = []
+    pending_act, node, inputs = "none", top, None
+    while node is not None:
+        nm = _name(node)
+        if nm in _ACT_NODES:
+            if pending_act != "none":
+                _unsupported("two activations in a row")
+            pending_act = _ACT_NODES[nm]
+            node = node.next_functions[0][0]
+            if node is None:
+                _unsupported("an activation applied to a constant")
+            continue
+        if nm == "AddmmBackward0":
+            if float(node._saved_alpha) != 1.0 or float(node._saved_beta) != 1.0:
+                _unsupported("addmm with alpha/beta != 1")
+            bias, nxt, weight = (_leaf_param(node.next_functions[0][0]), node.next_functions[1][0],
+                                 _leaf_param(node.next_functions[2][0]))
+            saved_in = node._saved_mat1
+            if bias is None:
+                _unsupported("a Linear layer with a frozen bias inside the differentiated part of the graph")
+        elif nm == "MmBackward0":
+            bias, nxt, weight = None, node.next_functions[0][0], _leaf_param(node.next_functions[1][0])
+            saved_in = node._saved_self
+        else:
+            _unsupported(f"graph node {nm}")
+        if weight is None:
+            _unsupported("a Linear layer with a frozen weight inside the differentiated part of the graph")
+        if weight.dim() != 2 or id(weight) not in offsets or (bias is not None and id(bias) not in offsets):
+            raise ValueError("the graph uses a trainable parameter that is not among the optimizer's parameters")
+        spec = LayerSpec(weight.shape[1], weight.shape[0], pending_act, bias is not None, offsets[id(weight)],
+                         offsets[id(bias)] if bias is not None else -1)
+        rev.append(spec)
+        pending_act = "none"
+        if nxt is None:
+            inputs = saved_in
+        node = nxt
+    if pending_act != "none" or not rev or inputs is None:
+        _unsupported("a graph that does not end in a Linear layer fed by constant inputs")
+    layers = rev[::-1]
+    used = {l.w_offset for l in layers} | {l.b_offset for l in layers if l.has_bias}
+    if used != set(offsets.values()):
+        raise ValueError("One of the optimizer's trainable parameters is not used in the graph of `loss`")
+    if inputs.dim() != 2:
+        _unsupported("Linear layers applied to inputs that are not [batch, features]")
+    if kind != "ce" and out_val is not None and tuple(targets.shape) != tuple(out_val.shape):
+        _unsupported("a loss with broadcast targets")
+    return Program(layers, kind, reduction, n_params, inputs=inputs, targets=targets)

@@ -1,0 +1,121 @@
+"""The linear system of one Newton step, resident on the device.
+
+A :class:`NativeProblem` bundles what the reference spreads over three closures
+(``forward``, ``grad``, ``mvp``; ``optimizer.py:584-597``): the lowered net, the linearisations of
+this rank's data chunks, the flat parameter vector, and -- when a process group is given -- the one
+exchange step of the data-parallel path: an all-reduce(sum) of the flat FP32 vector after the local
+chunk sum (gradient once per step, curvature product once per CG iteration, candidate losses once
+per batch of candidates).  Every rank then runs the identical fused vector update, so the replicas
+stay in lock-step without any scalar collective.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .native import Linearization, NativeNet
+
+
+def _all_reduce(t, group):
+    if group is not None:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+class NativeProblem:
+    def __init__(self, net: NativeNet, theta: torch.Tensor, curvature_opt: str,
+                 mvp_data: Sequence[Tuple[torch.Tensor, torch.Tensor]],
+                 grad_data: Optional[Sequence] = None, loss_data: Optional[Sequence] = None, group=None):
+        self.net, self.theta, self.curvature_opt, self.group = net, theta, curvature_opt, group
+        self.lib = _lib.load()
+        self.device = theta.device
+        hess = curvature_opt == "hessian"
+        self.mvp_lins: List[Linearization] = [net.linearize(x, t, hessian=hess) for x, t in mvp_data]
+        self.grad_lins = self.mvp_lins if grad_data is None else [net.linearize(x, t) for x, t in grad_data]
+        self.loss_lins = self.mvp_lins if loss_data is None else [net.linearize(x, t, loss_only=True) for x, t in loss_data]
+        self.n_mvp, self.n_grad, self.n_loss = (self._count(l) for l in (self.mvp_lins, self.grad_lins, self.loss_lins))
+        self._cand = torch.empty_like(theta)
+        self._linearized = False
+
+    def _count(self, lins):
+        n = torch.tensor([sum(l.n for l in lins)], dtype=torch.int64, device=self.device)
+        if self.group is not None:
+            _all_reduce(n, self.group)
+            return int(n.item())
+        return int(sum(l.n for l in lins))
+
+    # ---- once per step -----------------------------------------------------------------------------
+    def linearize(self):
+        """Forward passes at ``theta`` for the curvature (and gradient) chunks; returns the loss over
+        the curvature data as a float64 device scalar."""
+        acc = torch.zeros(1, dtype=torch.float64, device=self.device)
+        for lin in self.mvp_lins:
+            lin.forward(self.theta, self.n_mvp, acc)
+        if self.grad_lins is not self.mvp_lins:
+            for lin in self.grad_lins:
+                lin.forward(self.theta, self.n_grad, None)
+        _all_reduce(acc, self.group)
+        self._linearized = True
+        return acc
+
+    def gradient(self):
+        """Flat gradient over the gradient chunks (``optimizer.py:725-765``); also primes the Hessian path."""
+        assert self._linearized
+        g = torch.empty_like(self.theta)
+        for i, lin in enumerate(self.grad_lins):
+            lin.gradient(self.theta, g, accumulate=i > 0)
+        if self.curvature_opt == "hessian" and self.grad_lins is not self.mvp_lins:
+            scratch = torch.empty_like(self.theta)
+            for lin in self.mvp_lins:  # the Hessian product needs delta_l of its own chunks
+                lin.gradient(self.theta, scratch, accumulate=False)
+        _all_reduce(g, self.group)
+        return g
+
+    def fisher_diag(self):
+        """Empirical-Fisher diagonal over the curvature chunks."""
+        assert self._linearized
+        d = torch.empty_like(self.theta)
+        for i, lin in enumerate(self.mvp_lins):
+            lin.fisher(self.theta, d, accumulate=i > 0)
+        _all_reduce(d, self.group)
+        return d
+
+    # ---- once per CG iteration ---------------------------------------------------------------------
+    def matvec(self, v, out, skip_ptr=None):
+        """``out = B v`` (no damping), enqueued without host synchronisation."""
+        for i, lin in enumerate(self.mvp_lins):
+            if self.curvature_opt == "hessian":
+                lin.hessian(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)
+            else:
+                lin.ggn(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)
+        _all_reduce(out, self.group)
+
+    def mvp(self, v):
+        """Tensor-in / tensor-out form of :meth:`matvec` (the reference's ``mvp`` plug-in signature)."""
+        out = torch.empty_like(self.theta)
+        self.matvec(_lib.vec(v.detach().to(torch.float32)), out)
+        return out
+
+    # ---- step selection ----------------------------------------------------------------------------
+    def losses_at(self, steps):
+        """Loss over the loss chunks at ``theta + s`` for every candidate ``s``: one device pass, one
+        all-reduce, one device-to-host copy for the whole batch of candidates."""
+        acc = torch.zeros(len(steps), dtype=torch.float64, device=self.device)
+        for k, s in enumerate(steps):
+            s = _lib.vec(s.detach().to(torch.float32))
+            _lib.check(self.lib.hf_axpy_out(_lib.HF_F32, self.theta.numel(), self.theta.data_ptr(), 1.0, s.data_ptr(),
+                                            self._cand.data_ptr(), _lib.stream()))
+            for lin in self.loss_lins:
+                lin.forward(self._cand, self.n_loss, acc[k:])
+        _all_reduce(acc, self.group)
+        self._linearized = False  # activations now belong to a candidate point
+        return acc.to(torch.float32).tolist()
+
+    def target_function(self):
+        """``tfunc`` of ``optimizer.py:290-294`` with a batched variant attached as ``.many``."""
+        def f(step):
+            return self.losses_at([step])[0]
+
+        f.many = self.losses_at
+        return f

@@ -1,0 +1,102 @@
+"""CPU: host-side logic that needs no kernels -- lowering, snapshot grid, step selection, validation."""
+import warnings
+
+import pytest
+import torch
+from torch import nn
+
+from helpers import GOLDEN, SPECS, build_loss, build_model, make_data
+
+from pytorchhessianfree_b200 import HessianFree, cg_backtracking, cg_efficient_backtracking, cg_storing_grid, simple_linesearch
+from pytorchhessianfree_b200.cg import cg
+from pytorchhessianfree_b200.lowering import lower_graph, lower_module
+
+SEL = torch.load(f"{GOLDEN}/selection.pt", weights_only=False)
+CG = torch.load(f"{GOLDEN}/cg.pt", weights_only=False)
+
+
+def test_storing_grid_equals_reference():
+    for m, grid in CG["grids"].items():
+        assert cg_storing_grid(m) == grid
+    with pytest.raises(ValueError):
+        cg_storing_grid(10, gamma=0.5)
+
+
+def test_backtracking_toy_list():  # reference tests/test_cg_backtracking.py:16-44
+    assert cg_backtracking(lambda s: s, SEL["toy"]) == (1, 1.0)
+    assert cg_efficient_backtracking(lambda s: s, SEL["toy"]) == (4, 2.4)
+    assert cg_efficient_backtracking(lambda s: s, SEL["toy"], lookahead=3) == (4, 2.4)
+    f = lambda s: s  # noqa: E731
+    f.many = lambda ss: list(ss)
+    assert cg_efficient_backtracking(f, SEL["toy"], lookahead=4) == (4, 2.4)
+    assert cg_backtracking(f, SEL["toy"]) == (1, 1.0)
+
+
+def test_linesearch_matches_reference_fixture():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for c in SEL["linesearch"]:
+            f = lambda s: float(0.5 * s @ c["A"] @ s - c["b"] @ s)  # noqa: E731
+            a, fa = simple_linesearch(f, -c["b"], c["step"])
+            assert a == pytest.approx(c["alpha"]) and fa == pytest.approx(c["f"], rel=1e-5)
+    with pytest.raises(ValueError):
+        simple_linesearch(lambda s: 0.0, torch.zeros(2), torch.zeros(2), beta=1.0)
+    with pytest.raises(ValueError):
+        simple_linesearch(lambda s: 0.0, torch.zeros(2), torch.zeros(2), c=-1.0)
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+def test_graph_and_module_lowering_agree(name):
+    spec = SPECS[name]
+    torch.manual_seed(0)
+    model, loss_fn = build_model(spec), build_loss(spec, "sum")
+    x, t = make_data(spec, 5, 1)
+    params = [p for p in model.parameters() if p.requires_grad]
+    out = model(x)
+    g = lower_graph(loss_fn(out, t), out, params)
+    m = lower_module(model, loss_fn, params)
+    assert g.loss == m.loss == spec["loss"] and g.reduction == m.reduction == "sum"
+    assert g.n_params == m.n_params == sum(p.numel() for p in params)
+    # the graph only sees the differentiated suffix; frozen leading layers are folded into its inputs
+    gl, ml = g.layers, m.layers[len(m.layers) - len(g.layers):]
+    for a, b in zip(gl, ml):
+        assert (a.in_features, a.out_features, a.act, a.has_bias, a.w_offset, a.b_offset) == \
+               (b.in_features, b.out_features, b.act, b.has_bias, b.w_offset, b.b_offset)
+    assert g.inputs.shape == (5, gl[0].in_features)
+    assert torch.equal(g.targets, t)
+
+
+def test_unlowerable_graphs_are_refused_loudly():
+    p = torch.randn(4, requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        lower_graph((p ** 4).sum(), None, [p])
+    model = nn.Sequential(nn.Linear(4, 4), nn.Softplus(), nn.Linear(4, 2))
+    with pytest.raises(NotImplementedError):
+        lower_module(model, nn.MSELoss(), list(model.parameters()))
+    with pytest.raises(NotImplementedError):
+        lower_module(nn.Sequential(nn.Linear(4, 2)), nn.L1Loss(), [])
+
+
+def test_constructor_validation_matches_reference():  # reference optimizer.py:80-115
+    w = [nn.Parameter(torch.zeros(3))]
+    for kw in (dict(curvature_opt="fisher"), dict(damping=-1.0), dict(cg_max_iter=0), dict(lr=-0.1)):
+        with pytest.raises(ValueError):
+            HessianFree(w, **kw)
+    with pytest.raises(ValueError):
+        HessianFree([dict(params=w), dict(params=[nn.Parameter(torch.zeros(2))])])
+    with pytest.warns(UserWarning, match="won't get adapted"):
+        opt = HessianFree(w, damping=0.0)
+    assert opt.adapt_damping is False
+    opt = HessianFree(w)
+    assert set(opt.param_groups[0]) >= {"curvature_opt", "damping", "cg_max_iter", "lr"}
+    assert opt.param_groups[0]["damping"] == 1.0 and opt.param_groups[0]["cg_max_iter"] == 250
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cg(lambda v: v, torch.ones(4))
+    model = nn.Sequential(nn.Linear(3, 2))
+    opt = HessianFree(model.parameters())
+    x, t = torch.rand(4, 3), torch.rand(4, 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        opt.step(lambda: (lambda o: (nn.functional.mse_loss(o, t), o))(model(x)))
