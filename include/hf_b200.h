@@ -68,6 +68,8 @@ int hf_abi_version(void);
 const char* hf_last_error_string(void);
 /* number of SMs / co-resident CTAs the fused solver kernel will use on the current device */
 int hf_device_sm_count(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long hf_debug_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Fused PCG vector pass  (cg.py:186-224 + optimizer.py:266 + preconditioners.py:125)

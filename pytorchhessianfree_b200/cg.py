@@ -216,7 +216,8 @@ def pcg_device(matvec, b, x0=None, minv=None, damping=0.0, max_iter=250, tol=1e-
         s.init(Bp, x0, minv, damping, tol, atol, martens_conv_crit, False)
     x_first = s.x.clone() if 0 in keep else None
     slots = {it: k for k, it in enumerate(sorted(i for i in keep if 1 <= i <= max_iter))}
-    snaps = torch.empty((max(1, len(slots)), b.numel()), dtype=b.dtype, device=b.device)
+    row = (b.numel() + 3) // 4 * 4  # keep every snapshot row 16-byte aligned
+    snaps = torch.empty((max(1, len(slots)), row), dtype=b.dtype, device=b.device)[:, : b.numel()]
 
     hosts = [torch.empty(C.sizeof(PcgStatus), dtype=torch.uint8).pin_memory() for _ in range(2)]
     events = [torch.cuda.Event() for _ in range(2)]

@@ -7,6 +7,8 @@
 namespace hf {
 
 static thread_local char g_error[512] = "";
+static long long g_launches = 0;
+void note_launch() { ++g_launches; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -39,5 +41,6 @@ extern "C" {
 int hf_abi_version(void) { return HF_ABI_VERSION; }
 const char* hf_last_error_string(void) { return hf::g_error; }
 int hf_device_sm_count(void) { return hf::sm_count(); }
+long long hf_debug_launch_count(void) { return hf::g_launches; }
 
 }  // extern "C"

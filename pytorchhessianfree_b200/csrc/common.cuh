@@ -12,11 +12,19 @@ namespace hf {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
+void note_launch();
 
 #define HF_CUDA(expr)                                            \
   do {                                                           \
     cudaError_t e__ = (expr);                                    \
     if (e__ != cudaSuccess) return ::hf::cuda_fail(e__, #expr);  \
+  } while (0)
+
+// every kernel launch goes through one of these two, so hf_debug_launch_count() is exact
+#define HF_LAUNCH_CHECK()            \
+  do {                               \
+    ::hf::note_launch();             \
+    HF_CUDA(cudaGetLastError());     \
   } while (0)
 
 #define HF_REQUIRE(cond, code, ...)  \

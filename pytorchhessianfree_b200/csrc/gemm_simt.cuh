@@ -331,7 +331,7 @@ inline int launch_gemm_simt(GemmArgs g, cudaStream_t stream) {
     gemm_simt_kernel<128, 16, 8, 1><<<grid, kGemmThreads, 0, stream>>>(g, vA0, vB0, vA1, vB1);
   else
     gemm_simt_kernel<16, 128, 1, 8><<<grid, kGemmThreads, 0, stream>>>(g, vA0, vB0, vA1, vB1);
-  HF_CUDA(cudaGetLastError());
+  HF_LAUNCH_CHECK();
   return HF_OK;
 }
 

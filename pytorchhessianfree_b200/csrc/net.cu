@@ -258,7 +258,7 @@ static int weight_contraction(hf_lin* lin, int M, int N, int n_pairs, const Oper
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
   reduce_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, sp.splits, count, count, out, scale,
                                                               accumulate, skip);
-  HF_CUDA(cudaGetLastError());
+  HF_LAUNCH_CHECK();
   return HF_OK;
 }
 
@@ -269,10 +269,10 @@ static int bias_contraction(hf_lin* lin, const float* d, int cols, int square, f
   HF_REQUIRE((size_t)splits * cols <= lin->partial_floats, HF_ERR_WORKSPACE, "column-sum scratch too small");
   colsum_kernel<<<dim3((cols + 31) / 32, splits), dim3(32, 8), 0, stream>>>(d, lin->N, cols, cols, rows_per, square,
                                                                             lin->partial, skip);
-  HF_CUDA(cudaGetLastError());
+  HF_LAUNCH_CHECK();
   reduce_partials_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(lin->partial, splits, cols, cols, out, scale,
                                                                 accumulate, skip);
-  HF_CUDA(cudaGetLastError());
+  HF_LAUNCH_CHECK();
   return HF_OK;
 }
 
@@ -336,7 +336,7 @@ static int apply_loss_hessian(hf_lin* lin, float* rz, const int32_t* skip, cudaS
   int64_t blocks = (lin->N + 7) / 8;
   if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
   loss_hessian_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h);
-  HF_CUDA(cudaGetLastError());
+  HF_LAUNCH_CHECK();
   return HF_OK;
 }
 
@@ -573,10 +573,10 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
   int64_t blocks = (lin->N + 7) / 8;
   if (blocks > lin->loss_blocks) blocks = lin->loss_blocks;
   loss_forward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
-  HF_CUDA(cudaGetLastError());
+  HF_LAUNCH_CHECK();
   if (d_loss_acc) {
     loss_finalize_kernel<<<1, 256, 0, stream>>>(lin->loss_partial, (int)blocks, (double)a.scale, d_loss_acc);
-    HF_CUDA(cudaGetLastError());
+    HF_LAUNCH_CHECK();
   }
   lin->have_forward = true, lin->have_gradient = false;
   return HF_OK;

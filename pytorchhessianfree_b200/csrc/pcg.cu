@@ -463,6 +463,7 @@ static int launch_iter(int64_t P, void* d_state, int phase, const void* Bp, cons
   void* params[] = {&a};
   HF_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_iter_kernel<T>, dim3(g.n_ctas), dim3(kThreads), params, g.smem,
                                       stream));
+  note_launch();
   return HF_OK;
 }
 
@@ -491,6 +492,7 @@ static int launch_init(int64_t P, void* d_state, const void* Bx0, const void* x0
   void* params[] = {&a};
   HF_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_init_kernel<T>, dim3(g.n_ctas), dim3(kThreads), params, 0,
                                       stream));
+  note_launch();
   return HF_OK;
 }
 
@@ -561,7 +563,7 @@ int hf_precond_power(int dtype, int64_t P, const void* d_diag, double damping, d
         P, (const double*)d_diag, damping, -exponent, (double*)d_out);
   else
     HF_REQUIRE(false, HF_ERR_INVALID, "hf_precond_power: bad dtype");
-  HF_CUDA(cudaGetLastError());
+  HF_LAUNCH_CHECK();
   return HF_OK;
 }
 
@@ -578,7 +580,7 @@ int hf_axpy_out(int dtype, int64_t P, const void* d_a, double alpha, const void*
                                                                                    (const double*)d_b, (double*)d_out);
   else
     HF_REQUIRE(false, HF_ERR_INVALID, "hf_axpy_out: bad dtype");
-  HF_CUDA(cudaGetLastError());
+  HF_LAUNCH_CHECK();
   return HF_OK;
 }
 

@@ -177,7 +177,24 @@ def run_ref_steps(name, seed, reduction, curv, n_steps, n, precond, chunks=None,
         assert [int(b) for b in st["best_cg_iters"]] == [int(b) for b in orc.log["best_cg_iters"]]
     for p, q in zip(model.parameters(), twin.parameters()):
         same(p.data, q.data, "final params", tol=1e-6)
+    # the same trajectory in float64: how far the reference itself moves under rounding (test tolerances)
+    m64 = build_model(spec, torch.float64)
+    m64.load_state_dict({k: w.double() for k, w in init_state.items()})
+    o64 = O.OracleHF(m64.parameters(), curvature_opt=curv, **hf_kw)
+    for x, t in data:
+        x, t = x.double(), (t.double() if t.is_floating_point() else t)
+        M64 = O.diag_precond(O.ef_diag(m64, loss_fn, x, t, reduction), o64.damping) if precond else None
+        if chunks is None:
+            o64.step(lambda: (lambda o: (loss_fn(o, t), o))(m64(x)), M_func=M64)
+        else:
+            dl, off = [], 0
+            for c in chunks:
+                dl.append((x[off:off + c], t[off:off + c]))
+                off += c
+            o64.acc_step(m64, loss_fn, dl, M_func=M64, reduction=reduction)
     return dict(net=name, seed=seed, reduction=reduction, curv=curv, n=n, precond=precond, chunks=chunks, hf_kw=hf_kw,
+                init_losses64=list(o64.log["init_losses"]), num_cg_iters64=list(o64.log["num_cg_iters"]),
+                final_state64={k: w.detach().clone() for k, w in m64.state_dict().items()},
                 init_state=init_state, data=data, final_losses=finals,
                 init_losses=list(st["init_losses"]), dampings=list(st["dampings"]), cg_reasons=list(st["cg_reasons"]),
                 num_cg_iters=list(st["num_cg_iters"]), best_cg_iters=[int(b) for b in st["best_cg_iters"]],

@@ -1,0 +1,68 @@
+"""GPU: the stand-alone contraction ``hf_contract`` (the tile kernels every curvature product is made of)
+against a float64 torch matmul, for the three operand layouts, ragged shapes, two pairs and both engines."""
+import pytest
+import torch
+
+from pytorchhessianfree_b200 import _lib
+from pytorchhessianfree_b200._lib import Operand
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def run_contract(engine, A_list, B_list, layouts):
+    """A_list/B_list: logical [M,K] / [N,K] float32 tensors; layouts[i] = (a_kc, b_kc): True = K contiguous."""
+    lib = _lib.load()
+    M, K = A_list[0].shape
+    N = B_list[0].shape[0]
+    n = len(A_list)
+    keep, A, B = [], (Operand * n)(), (Operand * n)()
+    for i, (a, b, (a_kc, b_kc)) in enumerate(zip(A_list, B_list, layouts)):
+        for arr, t, kc in ((A, a, a_kc), (B, b, b_kc)):
+            if kc:
+                s = t.contiguous()
+                arr[i] = Operand(s.data_ptr(), s.shape[1], 1)
+            else:
+                s = t.t().contiguous()  # stored [K, MN]
+                arr[i] = Operand(s.data_ptr(), 1, s.shape[1])
+            keep.append(s)
+    C = torch.full((M, N), float("nan"), device=DEV)
+    rc = lib.hf_contract(engine, M, N, K, n, A, B, C.data_ptr(), N, None, 0, torch.cuda.current_stream().cuda_stream)
+    if rc == -2:
+        pytest.skip("shape not supported by this engine: " + lib.hf_last_error_string().decode())
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    return C
+
+
+SHAPES = [(16, 10, 10), (128, 128, 64), (512, 784, 512), (4096, 512, 784), (512, 784, 4096), (257, 67, 130),
+          (10, 512, 512), (512, 10, 512), (64, 64, 16), (300, 1000, 500), (1024, 1024, 8), (96, 200, 1000)]
+LAYOUTS = [(True, True), (True, False), (False, False), (False, True)]
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_single_pair(engine, shape, layout):
+    M, N, K = shape
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device=DEV, generator=g)
+    b = torch.randn(N, K, device=DEV, generator=g)
+    got = run_contract(engine, [a], [b], [layout])
+    want = a.double() @ b.double().t()
+    err = (got.double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-6 * max(1.0, (K / 512) ** 0.5), f"rel err {err:.2e}"  # FP32 accumulation grows ~sqrt(K)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("shape", [(512, 512, 784), (4096, 784, 512), (100, 36, 52), (512, 784, 1024)])
+@pytest.mark.parametrize("layout", LAYOUTS[:3])
+def test_two_pairs_accumulate(engine, shape, layout):
+    M, N, K = shape
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = [torch.randn(M, K, device=DEV, generator=g) for _ in range(2)]
+    b = [torch.randn(N, K, device=DEV, generator=g) for _ in range(2)]
+    got = run_contract(engine, a, b, [layout, layout])
+    want = a[0].double() @ b[0].double().t() + a[1].double() @ b[1].double().t()
+    err = (got.double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-6, f"rel err {err:.2e}"

@@ -1,5 +1,7 @@
 """GPU: loss, gradient, GGN-/Hessian-vector products and the Fisher diagonal of the sm_100a kernels against
 the fixtures minted from the reference (tests/golden/matvec.pt) -- tolerance rtol 1e-4 (north_star)."""
+import copy
+
 import pytest
 import torch
 
@@ -82,17 +84,26 @@ def test_wide_layers_against_oracle(widths, loss, n):
     """BASELINE.json configs[1]/[2] layer shapes (reduced batch) and a ragged-width net, against the CPU oracle."""
     spec = dict(widths=widths, act="relu" if loss == "ce" else "sigmoid", bias=[True] * (len(widths) - 1), frozen=[],
                 loss=loss, linear_after=[3] if loss == "bce" else [])
-    torch.manual_seed(0)
-    ref = build_model(spec)
     loss_fn = build_loss(spec, "mean")
-    x, t = make_data(spec, n, 11)
+    for seed in range(20):
+        # A ReLU whose pre-activation sits within rounding of 0 flips its mask between any two float32
+        # implementations (torch-CPU vs torch-CUDA differ there too); draw until no unit is that close.
+        torch.manual_seed(seed)
+        ref = build_model(spec)
+        x, t = make_data(spec, n, 11 + seed)
+        h, margin = x.double(), float("inf")
+        for m in copy.deepcopy(ref).double():
+            if isinstance(m, torch.nn.ReLU):
+                margin = min(margin, h.abs().min().item())
+            h = m(h)
+        if margin > 1e-5:
+            break
     params = [p for p in ref.parameters() if p.requires_grad]
     out = ref(x)
     l = loss_fn(out, t)
     v = torch.randn(sum(p.numel() for p in params))
     want_g = O.flatten(torch.autograd.grad(l, params, retain_graph=True))
     want_G, want_H = O.Gv(l, out, params, v), O.Hv(l, params, v)
-    import copy
     model = copy.deepcopy(ref).to(DEV)
     dparams = [p for p in model.parameters() if p.requires_grad]
     prog = lower_module(model, loss_fn, dparams)
