@@ -90,20 +90,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // UMMA shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46)
 // version[46,48)=1 layout_type[61,64)=2); all offsets in 16-byte units.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // operand tile of 128 (M or N) x 32 (K) floats at `base`, k-step ks (8 floats):
-//   K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); step = +32 B inside the swizzle row
-//   MN-major: 4 column blocks of [32 k-rows x 128 B], 4096 B apart (LBO); 8 k-rows = one 1024 B atom (SBO); step = +1024 B
+//   K-major : SWIZZLE_128B (type 2): rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); step = +32 B in the row
+//   MN-major: 32-bit operands only exist in SWIZZLE_128B_BASE32B (type 1; cute Layout_MN_SW128_32B_Atom, TMA
+//             SWIZZLE_128B_ATOM_32B): atoms of [4 k-rows x 128 B] 512 B apart along K (SBO); 4 column blocks of
+//             [32 k-rows x 128 B] 4096 B apart along MN (LBO); one k-step = 8 k-rows = +1024 B
 __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int mn_major, int ks) {
-  return mn_major ? smem_desc(base + ks * 1024, BKT * 128, 1024) : smem_desc(base + ks * 32, 16, 1024);
+  return mn_major ? smem_desc(base + ks * 1024, BKT * 128, 512, 1) : smem_desc(base + ks * 32, 16, 1024, 2);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -320,7 +322,9 @@ static int make_map(CUtensorMap* map, const Operand& op, int MN, int K) {
     box[0] = BKT, box[1] = BM;
   }
   CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(op.ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HF_REQUIRE(r == CUDA_SUCCESS, HF_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return HF_OK;

@@ -197,21 +197,33 @@ struct SplitPlan {
 };
 
 // split the batch dimension of a weight-gradient contraction so the grid fills the machine
-static SplitPlan plan_split(int M, int N, int64_t K) {
-  const TileChoice t = choose_tile(M, N);
-  const int64_t tiles = (int64_t)((M + t.bm - 1) / t.bm) * ((N + t.bn - 1) / t.bn);
-  const int64_t ktiles = (K + kBK - 1) / kBK;
-  int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
-  int64_t max_split = ktiles / 8;  // at least 8 k-tiles (128 samples) per split
+static SplitPlan plan_split(int M, int N, int64_t K, bool tensor_tiles) {
+  constexpr int kUnit = 32;  // K granularity both engines accept (tcgen05 k-block = 32, SIMT k-tile = 16)
+  int64_t tiles, want;
+  if (tensor_tiles) {  // 128x128 tiles, one CTA per SM: aim for just under one wave
+    tiles = (int64_t)((M + 127) / 128) * ((N + 127) / 128);
+    want = sm_count() / tiles;
+  } else {
+    const TileChoice t = choose_tile(M, N);
+    tiles = (int64_t)((M + t.bm - 1) / t.bm) * ((N + t.bn - 1) / t.bn);
+    want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+  }
+  const int64_t ktiles = (K + kUnit - 1) / kUnit;
+  int64_t max_split = ktiles / 4;  // at least 128 samples per split
   if (max_split < 1) max_split = 1;
   if (want > max_split) want = max_split;
   if (want > 64) want = 64;
   if (want < 1) want = 1;
   const int64_t kt_per = (ktiles + want - 1) / want;
   SplitPlan p;
-  p.k_per_split = (int)(kt_per * kBK);
+  p.k_per_split = (int)(kt_per * kUnit);
   p.splits = (int)((ktiles + kt_per - 1) / kt_per);
   return p;
+}
+
+// would a weight-gradient contraction [out,in] over `batch` samples run on the tensor-core tiles?
+static bool weight_on_tensor(const hf_net* net, int out, int in, int64_t batch, int square) {
+  return net->engine == 1 && !square && out >= 64 && in >= 64 && batch >= 16 && out % 4 == 0 && in % 4 == 0;
 }
 
 static int colsum_plan(int64_t rows) {
@@ -241,7 +253,7 @@ static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream) {
 // weight gradient (or its Fisher square): out[out,in] (+)= scale * sum_pairs A_s^T B_s over the batch
 static int weight_contraction(hf_lin* lin, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
                               float* out, float scale, int accumulate, const int32_t* skip, cudaStream_t stream) {
-  const SplitPlan sp = plan_split(M, N, lin->N);
+  const SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, square));
   HF_REQUIRE((size_t)sp.splits * M * N <= lin->partial_floats, HF_ERR_WORKSPACE, "split-K scratch too small");
   GemmArgs g = blank_gemm();
   g.M = M, g.N = N, g.K = (int)lin->N, g.n_pairs = n_pairs;
@@ -494,7 +506,11 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   if (!loss_only)
     for (int l = net->first_trainable; l < nl; ++l) {
       const Layer& L = net->L[l];
-      if (L.w_off >= 0) pf = std::max(pf, (size_t)plan_split(L.out, L.in, N).splits * L.out * L.in);
+      if (L.w_off >= 0) {
+        const int splits = std::max(plan_split(L.out, L.in, N, false).splits,
+                                    weight_on_tensor(net, L.out, L.in, N, 0) ? plan_split(L.out, L.in, N, true).splits : 1);
+        pf = std::max(pf, (size_t)splits * L.out * L.in);
+      }
       pf = std::max(pf, (size_t)colsum_plan(N) * L.out);
     }
   float* part = pf ? (float*)take(sizeof(float) * pf) : nullptr;

@@ -80,7 +80,8 @@ def test_chunked_equals_full_batch(name, curv):
 
 @pytest.mark.parametrize("widths,loss,n", [([784, 512, 512, 10], "ce", 512), ([784, 1000, 500, 250, 30, 250, 500, 1000, 784], "bce", 300),
                                             ([33, 130, 67, 9], "mse", 257)])
-def test_wide_layers_against_oracle(widths, loss, n):
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_wide_layers_against_oracle(widths, loss, n, engine):
     """BASELINE.json configs[1]/[2] layer shapes (reduced batch) and a ragged-width net, against the CPU oracle."""
     spec = dict(widths=widths, act="relu" if loss == "ce" else "sigmoid", bias=[True] * (len(widths) - 1), frozen=[],
                 loss=loss, linear_after=[3] if loss == "bce" else [])
@@ -108,7 +109,7 @@ def test_wide_layers_against_oracle(widths, loss, n):
     dparams = [p for p in model.parameters() if p.requires_grad]
     prog = lower_module(model, loss_fn, dparams)
     theta = torch.cat([p.detach().reshape(-1) for p in dparams])
-    net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params)
+    net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine)
     for curv, want in (("ggn", want_G), ("hessian", want_H)):
         prob = NativeProblem(net, theta, curv, [(x.to(DEV), t.to(DEV))])
         close(prob.linearize().float(), l.detach(), "loss", rtol=1e-5)
@@ -116,7 +117,8 @@ def test_wide_layers_against_oracle(widths, loss, n):
         close(prob.mvp(v.to(DEV)), want, curv)
 
 
-def test_linearity_and_symmetry_at_full_width():
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_linearity_and_symmetry_at_full_width(engine):
     """Size-independent properties at BASELINE configs[1] full size: B(av+bw) = aBv+bBw, v.Bw = w.Bv, v.Bv >= 0."""
     spec = dict(widths=[784, 512, 512, 10], act="relu", bias=[True] * 3, frozen=[], loss="ce")
     torch.manual_seed(0)
@@ -126,7 +128,8 @@ def test_linearity_and_symmetry_at_full_width():
     params = list(model.parameters())
     prog = lower_module(model, loss_fn, params)
     theta = torch.cat([p.detach().reshape(-1) for p in params])
-    prob = NativeProblem(NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params), theta, "ggn", [(x, t)])
+    prob = NativeProblem(NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine), theta, "ggn",
+                         [(x, t)])
     prob.linearize()
     v, w = torch.randn_like(theta), torch.randn_like(theta)
     Bv, Bw = prob.mvp(v), prob.mvp(w)
