@@ -221,12 +221,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) mbar_arrive(&full_lo[s]);
     }
     // ---------------- epilogue ----------------
+    // TMEM -> registers (one accumulator row per lane) -> shared (the pipeline buffers are idle once acc_full fired)
+    // -> row-wise, so that every global load/store of the fused epilogue is a coalesced 512-byte row segment.
     if (total > 0) {
       mbar_wait(acc_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const int m = m0 + warp * 32 + lane;  // TMEM lane == accumulator row
-    float* C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0);
+    constexpr int LDS_ROW = BN + 4;
+    float* stage = reinterpret_cast<float*>(tiles) + warp * 32 * LDS_ROW;
     for (int c = 0; c < BN; c += 16) {
       float v[16];
       if (total > 0) {
@@ -235,36 +237,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
-      if (m < g.M) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c + j;
-          if (n >= g.N) continue;
-          float x = v[j];
-          switch (g.epi) {
-            case EPI_STORE:
-              x = g.alpha * x + (g.bias ? g.bias[n] : 0.f);
-              break;
-            case EPI_BIAS_ACT:
-              x = act_apply(g.act, x + (g.bias ? g.bias[n] : 0.f));
-              break;
-            case EPI_BIAS_DACT:
-              x += g.bias ? g.bias[n] : 0.f;
-              if (g.C2) g.C2[(int64_t)m * g.ldc + n] = x;
-              if (g.act != HF_ACT_NONE) x *= act_d1(g.act, g.aux[(int64_t)m * g.ldaux + n]);
-              break;
-            case EPI_DACT:
-              if (g.C2) g.C2[(int64_t)m * g.ldc + n] = x;
-              if (g.act != HF_ACT_NONE) x *= act_d1(g.act, g.aux[(int64_t)m * g.ldaux + n]);
-              break;
-            case EPI_DACT_H: {
-              const float sv = g.act != HF_ACT_NONE ? g.aux[(int64_t)m * g.ldaux + n] : 0.f;
-              x = x * act_d1(g.act, sv);
-              if (g.h_ga) x += g.h_ga[(int64_t)m * g.ldaux + n] * act_d2(g.act, sv) * g.h_rz[(int64_t)m * g.ldaux + n];
-            } break;
-          }
-          C[(int64_t)m * g.ldc + n] = x;
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(stage + lane * LDS_ROW + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    __syncwarp();
+    float* C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(g.C2) | reinterpret_cast<uintptr_t>(g.aux) |
+                        reinterpret_cast<uintptr_t>(g.h_ga) | reinterpret_cast<uintptr_t>(g.h_rz) |
+                        reinterpret_cast<uintptr_t>(g.bias)) & 15u) == 0 && g.ldc % 4 == 0 && g.ldaux % 4 == 0;
+    const int n = n0 + lane * 4;
+    const int cnt = min(4, g.N - n);
+    const bool vec = al16 && cnt == 4;
+    auto load4 = [&](const float* p, float (&o)[4]) {
+      if (vec) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        o[0] = t.x, o[1] = t.y, o[2] = t.z, o[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = e < cnt ? p[e] : 0.f;
+      }
+    };
+    auto store4 = [&](float* p, const float (&o)[4]) {
+      if (vec) {
+        *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < cnt) p[e] = o[e];
+      }
+    };
+    if (cnt > 0) {
+      float bi[4] = {0.f, 0.f, 0.f, 0.f};
+      if (g.bias) load4(g.bias + n, bi);
+      const bool need_aux = g.act != HF_ACT_NONE && g.epi >= EPI_BIAS_DACT;
+      for (int r = 0; r < 32; ++r) {
+        const int m = m0 + warp * 32 + r;
+        if (m >= g.M) break;
+        float x[4], au[4] = {0.f, 0.f, 0.f, 0.f};
+        const float4 t = *reinterpret_cast<const float4*>(stage + r * LDS_ROW + lane * 4);
+        x[0] = t.x, x[1] = t.y, x[2] = t.z, x[3] = t.w;
+        if (need_aux) load4(g.aux + (int64_t)m * g.ldaux + n, au);
+        switch (g.epi) {
+          case EPI_STORE:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = g.alpha * x[e] + bi[e];
+            break;
+          case EPI_BIAS_ACT:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = act_apply(g.act, x[e] + bi[e]);
+            break;
+          case EPI_BIAS_DACT:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] += bi[e];
+            if (g.C2) store4(g.C2 + (int64_t)m * g.ldc + n, x);
+            if (need_aux)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
+            break;
+          case EPI_DACT:
+            if (g.C2) store4(g.C2 + (int64_t)m * g.ldc + n, x);
+            if (need_aux)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
+            break;
+          case EPI_DACT_H: {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
+            if (g.h_ga) {
+              float ga[4], rz[4];
+              load4(g.h_ga + (int64_t)m * g.ldaux + n, ga);
+              load4(g.h_rz + (int64_t)m * g.ldaux + n, rz);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] += ga[e] * act_d2(g.act, au[e]) * rz[e];
+            }
+          } break;
         }
+        store4(C + (int64_t)m * g.ldc + n, x);
       }
     }
   }
@@ -303,7 +352,7 @@ static bool operand_ok(const Operand& op, int MN, int K) {
 
 bool tc_supported(const GemmArgs& g) {
   if (g.square || g.n_pairs < 1 || g.n_pairs > 2) return false;
-  if (g.M < 64 || g.N < 64 || g.K < 16) return false;  // tiny layers stay on the SIMT tiles
+  if ((int64_t)g.M * g.N * g.K < kTcMinWork) return false;  // tiny layers stay on the SIMT tiles
   for (int s = 0; s < g.n_pairs; ++s)
     if (!operand_ok(g.A[s], g.M, g.K) || !operand_ok(g.B[s], g.N, g.K)) return false;
   return encode_fn() != nullptr;

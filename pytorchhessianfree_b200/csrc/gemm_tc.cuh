@@ -3,6 +3,8 @@
 #include "gemm_simt.cuh"
 
 namespace hf {
+// below this many multiply-adds a 128x128 tensor tile is mostly padding: stay on the SIMT tiles
+constexpr int64_t kTcMinWork = 1 << 20;
 bool tc_supported(const GemmArgs& g);
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t stream);
 }  // namespace hf

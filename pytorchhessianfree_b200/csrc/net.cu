@@ -62,6 +62,10 @@ namespace hf {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline bool curved(int act) { return act == HF_ACT_SIGMOID || act == HF_ACT_TANH; }
+// Every [batch, width] buffer the library owns is stored with its leading dimension rounded up to 4 floats
+// (16 B): TMA needs 16-byte row pitches, and this is what lets the 10-class output layer of the MLP config run on
+// the tensor-core tiles.  The padding columns are never read (all kernels bound their accesses by the width).
+static inline int pad4(int w) { return (w + 3) & ~3; }
 
 // ---- row-wise loss kernels ---------------------------------------------------------------------
 
@@ -70,6 +74,7 @@ struct LossArgs {
   const void* target;
   int64_t N;
   int C;
+  int ld;  // row pitch of out / prob / delta (targets are dense [N,C])
   int loss, final_act;
   float scale;    // 1/n_total (ce mean), 1/(n_total*C) (mse/bce mean), 1 (sum)
   float* prob;    // may be null
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(256) loss_forward_kernel(LossArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double block_loss = 0.0;
   for (int64_t n = (int64_t)blockIdx.x * 8 + warp; n < a.N; n += (int64_t)gridDim.x * 8) {
-    const float* z = a.out + n * a.C;
+    const float* z = a.out + n * a.ld;
     float row = 0.f;
     if (a.loss == HF_LOSS_SOFTMAX_CE) {
       const int64_t t = static_cast<const int64_t*>(a.target)[n];
@@ -98,8 +103,8 @@ __global__ void __launch_bounds__(256) loss_forward_kernel(LossArgs a) {
       const float lse = mx + logf(se);
       for (int c = lane; c < a.C; c += 32) {
         const float p = expf(z[c] - lse);
-        if (a.prob) a.prob[n * a.C + c] = p;
-        if (a.delta) a.delta[n * a.C + c] = a.scale * (p - (c == t ? 1.f : 0.f));
+        if (a.prob) a.prob[n * a.ld + c] = p;
+        if (a.delta) a.delta[n * a.ld + c] = a.scale * (p - (c == t ? 1.f : 0.f));
       }
       row = (t >= 0 && t < a.C) ? (lse - z[t]) : 0.f;  // every lane holds the same value
     } else {
@@ -116,9 +121,9 @@ __global__ void __launch_bounds__(256) loss_forward_kernel(LossArgs a) {
           const float p = 1.f / (1.f + expf(-zc));
           acc += fmaxf(zc, 0.f) - zc * tc + log1pf(expf(-fabsf(zc)));
           d = p - tc;
-          if (a.prob) a.prob[n * a.C + c] = p;
+          if (a.prob) a.prob[n * a.ld + c] = p;
         }
-        if (a.delta) a.delta[n * a.C + c] = a.scale * d * act_d1(a.final_act, zc);
+        if (a.delta) a.delta[n * a.ld + c] = a.scale * d * act_d1(a.final_act, zc);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -151,6 +156,7 @@ struct HessArgs {
   const float* out;
   int64_t N;
   int C;
+  int ld;
   int loss, final_act;
   float scale;
   const int32_t* skip;
@@ -160,9 +166,9 @@ __global__ void __launch_bounds__(256) loss_hessian_kernel(HessArgs a) {
   if (a.skip && *a.skip) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t n = (int64_t)blockIdx.x * 8 + warp; n < a.N; n += (int64_t)gridDim.x * 8) {
-    float* r = a.rz + n * a.C;
+    float* r = a.rz + n * a.ld;
     if (a.loss == HF_LOSS_SOFTMAX_CE) {
-      const float* p = a.prob + n * a.C;
+      const float* p = a.prob + n * a.ld;
       float dot = 0.f;
       for (int c = lane; c < a.C; c += 32) dot += p[c] * r[c];
 #pragma unroll
@@ -171,11 +177,11 @@ __global__ void __launch_bounds__(256) loss_hessian_kernel(HessArgs a) {
     } else if (a.loss == HF_LOSS_MSE) {
       for (int c = lane; c < a.C; c += 32) {
         float v = 2.f * a.scale * r[c];
-        if (a.final_act != HF_ACT_NONE) v *= act_d1(a.final_act, a.out[n * a.C + c]);
+        if (a.final_act != HF_ACT_NONE) v *= act_d1(a.final_act, a.out[n * a.ld + c]);
         r[c] = v;
       }
     } else {
-      const float* p = a.prob + n * a.C;
+      const float* p = a.prob + n * a.ld;
       for (int c = lane; c < a.C; c += 32) r[c] = a.scale * p[c] * (1.f - p[c]) * r[c];
     }
   }
@@ -223,7 +229,7 @@ static SplitPlan plan_split(int M, int N, int64_t K, bool tensor_tiles) {
 
 // would a weight-gradient contraction [out,in] over `batch` samples run on the tensor-core tiles?
 static bool weight_on_tensor(const hf_net* net, int out, int in, int64_t batch, int square) {
-  return net->engine == 1 && !square && out >= 64 && in >= 64 && batch >= 16 && out % 4 == 0 && in % 4 == 0;
+  return net->engine == 1 && !square && in % 4 == 0 && (int64_t)out * in * batch >= kTcMinWork;
 }
 
 static int colsum_plan(int64_t rows) {
@@ -274,12 +280,12 @@ static int weight_contraction(hf_lin* lin, int M, int N, int n_pairs, const Oper
   return HF_OK;
 }
 
-static int bias_contraction(hf_lin* lin, const float* d, int cols, int square, float* out, float scale, int accumulate,
-                            const int32_t* skip, cudaStream_t stream) {
+static int bias_contraction(hf_lin* lin, const float* d, int cols, int ld, int square, float* out, float scale,
+                            int accumulate, const int32_t* skip, cudaStream_t stream) {
   const int splits = colsum_plan(lin->N);
   const int rows_per = (int)((lin->N + splits - 1) / splits);
   HF_REQUIRE((size_t)splits * cols <= lin->partial_floats, HF_ERR_WORKSPACE, "column-sum scratch too small");
-  colsum_kernel<<<dim3((cols + 31) / 32, splits), dim3(32, 8), 0, stream>>>(d, lin->N, cols, cols, rows_per, square,
+  colsum_kernel<<<dim3((cols + 31) / 32, splits), dim3(32, 8), 0, stream>>>(d, lin->N, cols, ld, rows_per, square,
                                                                             lin->partial, skip);
   HF_LAUNCH_CHECK();
   reduce_partials_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(lin->partial, splits, cols, cols, out, scale,
@@ -304,27 +310,28 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
   for (int l = net->first_trainable; l < nl; ++l) {
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
+    const int ld_in = l == 0 ? L.in : pad4(L.in), ld_out = pad4(L.out);
     GemmArgs g = blank_gemm();
     g.M = (int)lin->N, g.N = L.out, g.K = L.in;
     int np = 0;
     if (L.w_off >= 0) {
-      g.A[np] = op_kc(a_in, L.in), g.B[np] = op_kc(v + L.w_off, L.in);
+      g.A[np] = op_kc(a_in, ld_in), g.B[np] = op_kc(v + L.w_off, L.in);
       ++np;
     }
     if (cur) {
-      g.A[np] = op_kc(cur, L.in), g.B[np] = op_kc(weight_ptr(L, theta), L.in);
+      g.A[np] = op_kc(cur, ld_in), g.B[np] = op_kc(weight_ptr(L, theta), L.in);
       ++np;
     }
     float* dst = (hessian && l < nl - 1) ? lin->ra[l] : lin->buf[which];
     if (np == 0) {
       // a frozen layer fed by a zero tangent contributes only its (frozen) nothing: R{z} = 0
-      HF_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * lin->N * L.out, stream));
+      HF_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * lin->N * ld_out, stream));
     } else {
       g.n_pairs = np;
-      g.C = dst, g.ldc = L.out;
+      g.C = dst, g.ldc = ld_out;
       g.epi = EPI_BIAS_DACT, g.act = L.act;
       g.bias = (L.has_bias && L.b_off >= 0) ? v + L.b_off : nullptr;
-      g.aux = lin->a[l], g.ldaux = L.out;
+      g.aux = lin->a[l], g.ldaux = ld_out;
       g.C2 = (hessian && curved(L.act)) ? lin->rz[l] : nullptr;
       g.skip = skip;
       int rc = run_gemm(net, g, stream);
@@ -342,7 +349,7 @@ static int apply_loss_hessian(hf_lin* lin, float* rz, const int32_t* skip, cudaS
   const hf_net* net = lin->net;
   HessArgs h;
   h.rz = rz, h.prob = lin->prob, h.out = lin->a.back();
-  h.N = lin->N, h.C = net->classes, h.loss = net->loss, h.final_act = net->L.back().act;
+  h.N = lin->N, h.C = net->classes, h.ld = pad4(net->classes), h.loss = net->loss, h.final_act = net->L.back().act;
   h.scale = loss_scale(net, lin->n_total);
   h.skip = skip;
   int64_t blocks = (lin->N + 7) / 8;
@@ -372,18 +379,19 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
   for (int l = nl - 1; l >= net->first_trainable; --l) {
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
+    const int ld_in = l == 0 ? L.in : pad4(L.in), ld_out = pad4(L.out);
     if (L.w_off >= 0) {
       Operand A[2], B[2];
       int np = 0;
-      A[np] = op_mnc(cur, L.out), B[np] = op_mnc(a_in, L.in), ++np;
+      A[np] = op_mnc(cur, ld_out), B[np] = op_mnc(a_in, ld_in), ++np;
       if (mode == BACK_HESSIAN && l > net->first_trainable) {
-        A[np] = op_mnc(lin->delta[l], L.out), B[np] = op_mnc(lin->ra[l - 1], L.in), ++np;
+        A[np] = op_mnc(lin->delta[l], ld_out), B[np] = op_mnc(lin->ra[l - 1], ld_in), ++np;
       }
       int rc = weight_contraction(lin, L.out, L.in, np, A, B, square, out + L.w_off, scale, accumulate, skip, stream);
       if (rc) return rc;
     }
     if (L.has_bias && L.b_off >= 0) {
-      int rc = bias_contraction(lin, cur, L.out, square, out + L.b_off, scale, accumulate, skip, stream);
+      int rc = bias_contraction(lin, cur, L.out, ld_out, square, out + L.b_off, scale, accumulate, skip, stream);
       if (rc) return rc;
     }
     if (l > net->first_trainable) {
@@ -391,15 +399,15 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       GemmArgs g = blank_gemm();
       g.M = (int)lin->N, g.N = L.in, g.K = L.out;
       int np = 0;
-      g.A[np] = op_kc(cur, L.out), g.B[np] = op_mnc(weight_ptr(L, theta), L.in), ++np;
+      g.A[np] = op_kc(cur, ld_out), g.B[np] = op_mnc(weight_ptr(L, theta), L.in), ++np;
       if (mode == BACK_HESSIAN && L.w_off >= 0) {
-        g.A[np] = op_kc(lin->delta[l], L.out), g.B[np] = op_mnc(v + L.w_off, L.in), ++np;
+        g.A[np] = op_kc(lin->delta[l], ld_out), g.B[np] = op_mnc(v + L.w_off, L.in), ++np;
       }
       g.n_pairs = np;
       float* dst = keep ? lin->delta[l - 1] : lin->buf[which];
-      g.C = dst, g.ldc = L.in;
+      g.C = dst, g.ldc = ld_in;
       g.act = Lp.act;
-      g.aux = lin->a[l - 1], g.ldaux = L.in;
+      g.aux = lin->a[l - 1], g.ldaux = ld_in;
       if (mode == BACK_HESSIAN) {
         g.epi = EPI_DACT_H;
         if (curved(Lp.act)) g.h_ga = lin->ga[l - 1], g.h_rz = lin->rz[l - 1];
@@ -445,7 +453,7 @@ int hf_net_create(const hf_layer_desc* layers, int32_t n_layers, int32_t loss, i
     Layer l{d.in_features, d.out_features, d.act, d.has_bias, d.w_offset, d.has_bias ? d.b_offset : -1, d.d_w_frozen,
             d.d_b_frozen};
     if (net->first_trainable < 0 && (l.w_off >= 0 || l.b_off >= 0)) net->first_trainable = i;
-    net->max_width = std::max(net->max_width, std::max(l.in, l.out));
+    net->max_width = std::max(net->max_width, std::max(l.in, pad4(l.out)));
     net->L.push_back(l);
   }
   net->classes = net->L.back().out;
@@ -489,15 +497,15 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       for (int l = 0; l < nl; ++l) lin->a[l] = (l & 1) ? b1 : b0;
   } else {
     for (int l = 0; l < nl; ++l) {
-      float* p = (float*)take(sizeof(float) * N * net->L[l].out);
+      float* p = (float*)take(sizeof(float) * N * pad4(net->L[l].out));
       if (lin) lin->a[l] = p;
     }
   }
   float* prob = nullptr;
   float* dL = nullptr;
   if (!loss_only) {
-    if (net->loss != HF_LOSS_MSE) prob = (float*)take(sizeof(float) * N * net->classes);
-    dL = (float*)take(sizeof(float) * N * net->classes);
+    if (net->loss != HF_LOSS_MSE) prob = (float*)take(sizeof(float) * N * pad4(net->classes));
+    dL = (float*)take(sizeof(float) * N * pad4(net->classes));
   }
   float* b0 = loss_only ? nullptr : (float*)take(sizeof(float) * N * net->max_width);
   float* b1 = loss_only ? nullptr : (float*)take(sizeof(float) * N * net->max_width);
@@ -519,7 +527,7 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   double* lp = (double*)take(sizeof(double) * lb);
   if (hess && !loss_only) {
     for (int l = net->first_trainable; l < nl; ++l) {
-      const size_t bytes = sizeof(float) * N * net->L[l].out;
+      const size_t bytes = sizeof(float) * N * pad4(net->L[l].out);
       float* d = (l < nl - 1) ? (float*)take(bytes) : nullptr;  // the last layer's delta is deltaL
       float* r = (l < nl - 1) ? (float*)take(bytes) : nullptr;
       float* g = nullptr;
@@ -574,15 +582,15 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     const Layer& L = net->L[l];
     GemmArgs g = blank_gemm();
     g.M = (int)lin->N, g.N = L.out, g.K = L.in, g.n_pairs = 1;
-    g.A[0] = op_kc(l == 0 ? d_x : lin->a[l - 1], L.in);
+    g.A[0] = op_kc(l == 0 ? d_x : lin->a[l - 1], l == 0 ? L.in : pad4(L.in));
     g.B[0] = op_kc(weight_ptr(L, d_theta), L.in);
-    g.C = lin->a[l], g.ldc = L.out;
+    g.C = lin->a[l], g.ldc = pad4(L.out);
     g.epi = EPI_BIAS_ACT, g.act = L.act, g.bias = bias_ptr(L, d_theta);
     int rc = run_gemm(net, g, stream);
     if (rc) return rc;
   }
   LossArgs a;
-  a.out = lin->a.back(), a.target = d_targets, a.N = lin->N, a.C = net->classes;
+  a.out = lin->a.back(), a.target = d_targets, a.N = lin->N, a.C = net->classes, a.ld = pad4(net->classes);
   a.loss = net->loss, a.final_act = net->L.back().act;
   a.scale = loss_scale(net, n_total);
   a.prob = lin->prob, a.delta = lin->deltaL, a.partial = lin->loss_partial;

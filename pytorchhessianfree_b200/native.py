@@ -138,5 +138,6 @@ class Linearization:
         """The network outputs of the last forward pass, as a tensor view (tests)."""
         p = self.lib.hf_lin_logits(self.handle)
         off = (p - self.workspace.data_ptr()) // 4
-        flat = self.workspace.view(torch.float32) if self.workspace.data_ptr() % 4 == 0 else None
-        return flat[off: off + self.n * self.net.classes].view(self.n, self.net.classes)
+        ld = (self.net.classes + 3) // 4 * 4  # library-owned [batch, width] buffers are pitched to 16 bytes
+        flat = self.workspace.view(torch.float32)
+        return flat[off: off + self.n * ld].view(self.n, ld)[:, : self.net.classes]
