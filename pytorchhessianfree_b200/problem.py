@@ -13,14 +13,9 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from .dist import all_reduce_sum as _all_reduce
+from .dist import global_count
 from .native import Linearization, NativeNet
-
-
-def _all_reduce(t, group):
-    if group is not None:
-        import torch.distributed as dist
-
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
 class NativeProblem:
@@ -39,11 +34,7 @@ class NativeProblem:
         self._linearized = False
 
     def _count(self, lins):
-        n = torch.tensor([sum(l.n for l in lins)], dtype=torch.int64, device=self.device)
-        if self.group is not None:
-            _all_reduce(n, self.group)
-            return int(n.item())
-        return int(sum(l.n for l in lins))
+        return global_count(sum(l.n for l in lins), self.group, self.device)
 
     # ---- once per step -----------------------------------------------------------------------------
     def linearize(self):
