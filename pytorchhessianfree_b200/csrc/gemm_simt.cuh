@@ -46,6 +46,7 @@ struct GemmArgs {
   int split_k;      // gridDim.z; partial z goes to C + z * M * ldc
   int k_per_split;  // multiple of BK
   const int32_t* skip;
+  float* colpart;  // tensor-core engine only: colpart[blockIdx.y * N + n] = column sums of the stored tile rows
 };
 
 __device__ __forceinline__ float act_apply(int act, float z) {
@@ -263,6 +264,26 @@ static __global__ void reduce_partials_kernel(const float* __restrict__ part, in
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[(int64_t)z * stride + i];
     out[i] = (accumulate ? out[i] : 0.f) + scale * s;
+  }
+}
+
+// Two reductions in one launch: a weight-gradient slice and the bias slice that follows it in the flat layout.
+static __global__ void reduce_partials2_kernel(const float* __restrict__ partW, int splitsW, int64_t countW,
+                                               float* __restrict__ outW, const float* __restrict__ partB, int splitsB,
+                                               int64_t countB, float* __restrict__ outB, float scale, int accumulate,
+                                               const int32_t* __restrict__ skip) {
+  if (skip && *skip) return;
+  const int64_t total = countW + countB;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool w = i < countW;
+    const int64_t j = w ? i : i - countW;
+    const float* part = w ? partW : partB;
+    const int64_t stride = w ? countW : countB;
+    const int splits = w ? splitsW : splitsB;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * stride + j];
+    float* out = w ? outW : outB;
+    out[j] = (accumulate ? out[j] : 0.f) + scale * s;
   }
 }
 

@@ -267,53 +267,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (e < cnt) p[e] = o[e];
       }
     };
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of what this lane stores (bias gradient of the next layer)
     if (cnt > 0) {
       float bi[4] = {0.f, 0.f, 0.f, 0.f};
       if (g.bias) load4(g.bias + n, bi);
       const bool need_aux = g.act != HF_ACT_NONE && g.epi >= EPI_BIAS_DACT;
-      for (int r = 0; r < 32; ++r) {
-        const int m = m0 + warp * 32 + r;
-        if (m >= g.M) break;
-        float x[4], au[4] = {0.f, 0.f, 0.f, 0.f};
-        const float4 t = *reinterpret_cast<const float4*>(stage + r * LDS_ROW + lane * 4);
-        x[0] = t.x, x[1] = t.y, x[2] = t.z, x[3] = t.w;
-        if (need_aux) load4(g.aux + (int64_t)m * g.ldaux + n, au);
-        switch (g.epi) {
-          case EPI_STORE:
+      constexpr int RB = 8;  // rows in flight: all their global loads are issued before the first use
+      for (int r0 = 0; r0 < 32; r0 += RB) {
+        float aub[RB][4];
+        if (need_aux) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = g.alpha * x[e] + bi[e];
-            break;
-          case EPI_BIAS_ACT:
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = act_apply(g.act, x[e] + bi[e]);
-            break;
-          case EPI_BIAS_DACT:
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] += bi[e];
-            if (g.C2) store4(g.C2 + (int64_t)m * g.ldc + n, x);
-            if (need_aux)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
-            break;
-          case EPI_DACT:
-            if (g.C2) store4(g.C2 + (int64_t)m * g.ldc + n, x);
-            if (need_aux)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
-            break;
-          case EPI_DACT_H: {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
-            if (g.h_ga) {
-              float ga[4], rz[4];
-              load4(g.h_ga + (int64_t)m * g.ldaux + n, ga);
-              load4(g.h_rz + (int64_t)m * g.ldaux + n, rz);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] += ga[e] * act_d2(g.act, au[e]) * rz[e];
-            }
-          } break;
+          for (int j = 0; j < RB; ++j) {
+            const int mj = m0 + warp * 32 + r0 + j;
+            if (mj < g.M) load4(g.aux + (int64_t)mj * g.ldaux + n, aub[j]);
+          }
         }
-        store4(C + (int64_t)m * g.ldc + n, x);
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          const int r = r0 + j;
+          const int m = m0 + warp * 32 + r;
+          if (m >= g.M) break;
+          float x[4], au[4] = {0.f, 0.f, 0.f, 0.f};
+          const float4 t = *reinterpret_cast<const float4*>(stage + r * LDS_ROW + lane * 4);
+          x[0] = t.x, x[1] = t.y, x[2] = t.z, x[3] = t.w;
+          if (need_aux) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) au[e] = aub[j][e];
+          }
+          switch (g.epi) {
+            case EPI_STORE:
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = g.alpha * x[e] + bi[e];
+              break;
+            case EPI_BIAS_ACT:
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = act_apply(g.act, x[e] + bi[e]);
+              break;
+            case EPI_BIAS_DACT:
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] += bi[e];
+              if (g.C2) store4(g.C2 + (int64_t)m * g.ldc + n, x);
+              if (need_aux)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
+              break;
+            case EPI_DACT:
+              if (g.C2) store4(g.C2 + (int64_t)m * g.ldc + n, x);
+              if (need_aux)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
+              break;
+            case EPI_DACT_H: {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
+              if (g.h_ga) {
+                float ga[4], rz[4];
+                load4(g.h_ga + (int64_t)m * g.ldaux + n, ga);
+                load4(g.h_rz + (int64_t)m * g.ldaux + n, rz);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] += ga[e] * act_d2(g.act, au[e]) * rz[e];
+              }
+            } break;
+          }
+          store4(C + (int64_t)m * g.ldc + n, x);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) cs[e] += x[e];
+        }
+      }
+    }
+    if (g.colpart) {
+      // 4 warps x 32 rows -> one row of column sums per CTA, fixed order (deterministic)
+      float* red = reinterpret_cast<float*>(tiles) + 4 * 32 * (BN + 4);
+      *reinterpret_cast<float4*>(red + warp * BN + lane * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 0) {
+        const int n = n0 + lane * 4;
+  #pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = lane * 4 + e;
+          const float t = (red[idx] + red[BN + idx]) + (red[2 * BN + idx] + red[3 * BN + idx]);
+          if (n + e < g.N) g.colpart[(int64_t)blockIdx.y * g.N + n + e] = t;
+        }
       }
     }
   }

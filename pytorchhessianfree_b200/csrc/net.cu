@@ -52,6 +52,8 @@ struct hf_lin {
   float* buf[2];              // ping-pong [N,max_width]
   float* partial;             // split-K partial tiles
   size_t partial_floats;
+  float* colbuf;              // column-sum partials (bias gradients): [row blocks][width]
+  size_t colbuf_floats;
   double* loss_partial;
   int loss_blocks;
   int64_t n_total;
@@ -251,45 +253,53 @@ static GemmArgs blank_gemm() {
 }
 
 // dispatch one contraction to the tensor-core engine when the net asks for it and the shape fits
-static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream) {
-  if (net->engine == 1 && tc_supported(g)) return launch_gemm_tc(g, stream);
-  return launch_gemm_simt(g, stream);
+static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream, bool* on_tensor = nullptr) {
+  const bool tc = net->engine == 1 && tc_supported(g);
+  if (on_tensor) *on_tensor = tc;
+  return tc ? launch_gemm_tc(g, stream) : launch_gemm_simt(g, stream);
 }
 
-// weight gradient (or its Fisher square): out[out,in] (+)= scale * sum_pairs A_s^T B_s over the batch
-static int weight_contraction(hf_lin* lin, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
-                              float* out, float scale, int accumulate, const int32_t* skip, cudaStream_t stream) {
-  const SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, square));
-  HF_REQUIRE((size_t)sp.splits * M * N <= lin->partial_floats, HF_ERR_WORKSPACE, "split-K scratch too small");
-  GemmArgs g = blank_gemm();
-  g.M = M, g.N = N, g.K = (int)lin->N, g.n_pairs = n_pairs;
-  for (int s = 0; s < n_pairs; ++s) g.A[s] = A[s], g.B[s] = B[s];
-  g.square = square;
-  g.C = lin->partial, g.ldc = N;
-  g.epi = EPI_STORE;
-  g.split_k = sp.splits, g.k_per_split = sp.k_per_split;
-  g.skip = skip;
-  int rc = run_gemm(lin->net, g, stream);
-  if (rc) return rc;
-  const int64_t count = (int64_t)M * N;
-  int64_t blocks = (count + 255) / 256;
+// Gradient slices of one layer: out_W[out,in] (+)= scale * sum_pairs A_s^T B_s over the batch (split-K partials),
+// out_b[out] (+)= scale * column sums of d.  The column sums either come for free from the tensor-core kernel that
+// produced d (`col_tiles` partial rows already in lin->colbuf) or from one colsum launch; ONE launch then reduces
+// both partial sets in fixed order (deterministic) into the flat vector.
+static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
+                          float* out_w, const float* d, int ld_d, int col_tiles, float* out_b, float scale, int accumulate,
+                          const int32_t* skip, cudaStream_t stream) {
+  int splits_w = 0, splits_b = 0;
+  if (out_w) {
+    const SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, square));
+    HF_REQUIRE((size_t)sp.splits * M * N <= lin->partial_floats, HF_ERR_WORKSPACE, "split-K scratch too small");
+    GemmArgs g = blank_gemm();
+    g.M = M, g.N = N, g.K = (int)lin->N, g.n_pairs = n_pairs;
+    for (int s = 0; s < n_pairs; ++s) g.A[s] = A[s], g.B[s] = B[s];
+    g.square = square;
+    g.C = lin->partial, g.ldc = N;
+    g.epi = EPI_STORE;
+    g.split_k = sp.splits, g.k_per_split = sp.k_per_split;
+    g.skip = skip;
+    int rc = run_gemm(lin->net, g, stream);
+    if (rc) return rc;
+    splits_w = sp.splits;
+  }
+  if (out_b) {
+    if (col_tiles > 0) {
+      splits_b = col_tiles;
+    } else {
+      splits_b = colsum_plan(lin->N);
+      const int rows_per = (int)((lin->N + splits_b - 1) / splits_b);
+      HF_REQUIRE((size_t)splits_b * M <= lin->colbuf_floats, HF_ERR_WORKSPACE, "column-sum scratch too small");
+      colsum_kernel<<<dim3((M + 31) / 32, splits_b), dim3(32, 8), 0, stream>>>(d, lin->N, M, ld_d, rows_per, square,
+                                                                                lin->colbuf, skip);
+      HF_LAUNCH_CHECK();
+    }
+  }
+  const int64_t count_w = out_w ? (int64_t)M * N : 0, count_b = out_b ? M : 0;
+  if (count_w + count_b == 0) return HF_OK;
+  int64_t blocks = (count_w + count_b + 255) / 256;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, sp.splits, count, count, out, scale,
-                                                              accumulate, skip);
-  HF_LAUNCH_CHECK();
-  return HF_OK;
-}
-
-static int bias_contraction(hf_lin* lin, const float* d, int cols, int ld, int square, float* out, float scale,
-                            int accumulate, const int32_t* skip, cudaStream_t stream) {
-  const int splits = colsum_plan(lin->N);
-  const int rows_per = (int)((lin->N + splits - 1) / splits);
-  HF_REQUIRE((size_t)splits * cols <= lin->partial_floats, HF_ERR_WORKSPACE, "column-sum scratch too small");
-  colsum_kernel<<<dim3((cols + 31) / 32, splits), dim3(32, 8), 0, stream>>>(d, lin->N, cols, ld, rows_per, square,
-                                                                            lin->partial, skip);
-  HF_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(lin->partial, splits, cols, cols, out, scale,
-                                                                accumulate, skip);
+  reduce_partials2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, splits_w, count_w, out_w, lin->colbuf,
+                                                               splits_b, count_b, out_b, scale, accumulate, skip);
   HF_LAUNCH_CHECK();
   return HF_OK;
 }
@@ -375,25 +385,25 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
   float scale = 1.f;
   if (mode == BACK_FISHER && net->reduction == HF_RED_MEAN) scale = (float)lin->n_total;
   const float* cur = top;
+  int cur_col_tiles = 0;  // > 0: the kernel that produced `cur` also left its column sums in lin->colbuf
   int which = top_buf >= 0 ? (top_buf ^ 1) : 0;  // next free ping-pong buffer
   for (int l = nl - 1; l >= net->first_trainable; --l) {
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
     const int ld_in = l == 0 ? L.in : pad4(L.in), ld_out = pad4(L.out);
-    if (L.w_off >= 0) {
+    {
       Operand A[2], B[2];
       int np = 0;
       A[np] = op_mnc(cur, ld_out), B[np] = op_mnc(a_in, ld_in), ++np;
       if (mode == BACK_HESSIAN && l > net->first_trainable) {
         A[np] = op_mnc(lin->delta[l], ld_out), B[np] = op_mnc(lin->ra[l - 1], ld_in), ++np;
       }
-      int rc = weight_contraction(lin, L.out, L.in, np, A, B, square, out + L.w_off, scale, accumulate, skip, stream);
+      const bool has_b = L.has_bias && L.b_off >= 0;
+      int rc = layer_gradient(lin, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
+                              cur_col_tiles, has_b ? out + L.b_off : nullptr, scale, accumulate, skip, stream);
       if (rc) return rc;
     }
-    if (L.has_bias && L.b_off >= 0) {
-      int rc = bias_contraction(lin, cur, L.out, ld_out, square, out + L.b_off, scale, accumulate, skip, stream);
-      if (rc) return rc;
-    }
+    cur_col_tiles = 0;
     if (l > net->first_trainable) {
       const Layer& Lp = net->L[l - 1];
       GemmArgs g = blank_gemm();
@@ -416,8 +426,13 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
         g.C2 = (keep && curved(Lp.act)) ? lin->ga[l - 1] : nullptr;
       }
       g.skip = skip;
-      int rc = run_gemm(net, g, stream);
+      const int row_tiles = (int)((lin->N + 127) / 128);
+      const bool want_cols = !square && Lp.has_bias && Lp.b_off >= 0 && (size_t)row_tiles * L.in <= lin->colbuf_floats;
+      g.colpart = want_cols ? lin->colbuf : nullptr;
+      bool on_tensor = false;
+      int rc = run_gemm(net, g, stream, &on_tensor);
       if (rc) return rc;
+      cur_col_tiles = (want_cols && on_tensor) ? row_tiles : 0;
       cur = dst;
       if (!keep) which ^= 1;
     }
@@ -522,6 +537,8 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       pf = std::max(pf, (size_t)colsum_plan(N) * L.out);
     }
   float* part = pf ? (float*)take(sizeof(float) * pf) : nullptr;
+  const size_t cf = loss_only ? 0 : (size_t)std::max<int64_t>(colsum_plan(N), (N + 127) / 128) * net->max_width;
+  float* colb = cf ? (float*)take(sizeof(float) * cf) : nullptr;
   int64_t lb = (N + 7) / 8;
   if (lb > 1024) lb = 1024;
   double* lp = (double*)take(sizeof(double) * lb);
@@ -538,6 +555,7 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   }
   if (lin) {
     lin->prob = prob, lin->deltaL = dL, lin->buf[0] = b0, lin->buf[1] = b1;
+    lin->colbuf = colb, lin->colbuf_floats = cf;
     lin->partial = part, lin->partial_floats = pf, lin->loss_partial = lp, lin->loss_blocks = (int)lb;
   }
   return off;
