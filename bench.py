@@ -358,7 +358,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("HF_ENGINE", "simt"), choices=["simt", "tc"])
+    ap.add_argument("--engine", default=os.environ.get("HF_ENGINE", "tc"), choices=["simt", "tc"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

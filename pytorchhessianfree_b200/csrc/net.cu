@@ -7,6 +7,7 @@
 //   hf_fisher_diag                    <- diag_EF_backpack, preconditioners.py:11-60
 // Activations are computed once per linearisation and stay resident in HBM for the whole solve (the
 // reference re-runs the forward pass for every chunk on every CG iteration, optimizer.py:805-814).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -50,10 +51,18 @@ struct hf_lin {
   float* prob;                // [N,C] softmax / sigmoid probabilities
   float* deltaL;              // [N,C] dloss/dz of the last layer
   float* buf[2];              // ping-pong [N,max_width]
+  float* partial_fwd;         // split-K partial tiles of the last R-op layer when the output is narrow
+  int fwd_splits_max;
   float* partial;             // split-K partial tiles
   size_t partial_floats;
-  float* colbuf;              // column-sum partials (bias gradients): [row blocks][width]
-  size_t colbuf_floats;
+  int fwd_splits;             // > 0: the last rop_forward left split partials in partial_fwd
+  const float* fwd_bias;
+  std::vector<float*> cot;    // cot[l]: cotangent dloss/dz_l (or its R-derivative) of the sweep in flight
+  std::vector<float*> colbuf; // colbuf[l]: column-sum partials of cot[l] (bias gradient): [row blocks][out_l]
+  size_t col_rows;            // row blocks each colbuf[l] can hold
+  cudaStream_t side;          // weight/bias gradients of layer l run here, concurrently with the data product that
+  std::vector<cudaEvent_t> ev;  // continues the sweep on the caller's stream (ev[l]: cot[l] is ready)
+  cudaEvent_t join;
   double* loss_partial;
   int loss_blocks;
   int64_t n_total;
@@ -162,6 +171,11 @@ struct HessArgs {
   int loss, final_act;
   float scale;
   const int32_t* skip;
+  // optional: R{output} arrives as split-K partial tiles part[s][n][c] (+ bias[c]) instead of in rz
+  const float* part;
+  int splits;
+  int64_t part_stride;
+  const float* bias;
 };
 
 __global__ void __launch_bounds__(256) loss_hessian_kernel(HessArgs a) {
@@ -169,6 +183,13 @@ __global__ void __launch_bounds__(256) loss_hessian_kernel(HessArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t n = (int64_t)blockIdx.x * 8 + warp; n < a.N; n += (int64_t)gridDim.x * 8) {
     float* r = a.rz + n * a.ld;
+    if (a.part) {
+      for (int c = lane; c < a.C; c += 32) {  // each lane only ever touches its own columns: no sync needed
+        float t = a.bias ? a.bias[c] : 0.f;
+        for (int z = 0; z < a.splits; ++z) t += a.part[z * a.part_stride + n * a.ld + c];
+        r[c] = t;
+      }
+    }
     if (a.loss == HF_LOSS_SOFTMAX_CE) {
       const float* p = a.prob + n * a.ld;
       float dot = 0.f;
@@ -264,8 +285,8 @@ static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream, b
 // produced d (`col_tiles` partial rows already in lin->colbuf) or from one colsum launch; ONE launch then reduces
 // both partial sets in fixed order (deterministic) into the flat vector.
 static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
-                          float* out_w, const float* d, int ld_d, int col_tiles, float* out_b, float scale, int accumulate,
-                          const int32_t* skip, cudaStream_t stream) {
+                          float* out_w, const float* d, int ld_d, int col_tiles, float* colbuf, float* out_b, float scale,
+                          int accumulate, const int32_t* skip, cudaStream_t stream) {
   int splits_w = 0, splits_b = 0;
   if (out_w) {
     const SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, square));
@@ -288,9 +309,9 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
     } else {
       splits_b = colsum_plan(lin->N);
       const int rows_per = (int)((lin->N + splits_b - 1) / splits_b);
-      HF_REQUIRE((size_t)splits_b * M <= lin->colbuf_floats, HF_ERR_WORKSPACE, "column-sum scratch too small");
+      HF_REQUIRE((size_t)splits_b <= lin->col_rows, HF_ERR_WORKSPACE, "column-sum scratch too small");
       colsum_kernel<<<dim3((M + 31) / 32, splits_b), dim3(32, 8), 0, stream>>>(d, lin->N, M, ld_d, rows_per, square,
-                                                                                lin->colbuf, skip);
+                                                                                colbuf, skip);
       HF_LAUNCH_CHECK();
     }
   }
@@ -298,8 +319,8 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
   if (count_w + count_b == 0) return HF_OK;
   int64_t blocks = (count_w + count_b + 255) / 256;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  reduce_partials2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, splits_w, count_w, out_w, lin->colbuf,
-                                                               splits_b, count_b, out_b, scale, accumulate, skip);
+  reduce_partials2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, splits_w, count_w, out_w, colbuf, splits_b,
+                                                               count_b, out_b, scale, accumulate, skip);
   HF_LAUNCH_CHECK();
   return HF_OK;
 }
@@ -333,6 +354,28 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
       ++np;
     }
     float* dst = (hessian && l < nl - 1) ? lin->ra[l] : lin->buf[which];
+    lin->fwd_splits = 0;
+    if (l == nl - 1 && np > 0 && lin->partial_fwd && L.act == HF_ACT_NONE && net->engine == 1) {
+      // Narrow output layer (10 classes): a 128x128 tensor tile per 128 rows would leave most SMs idle, so the
+      // contraction is split over K instead and the loss-Hessian kernel sums the partial tiles (+ bias tangent).
+      const int row_tiles = (int)((lin->N + 127) / 128);
+      const int kb = (L.in + 31) / 32;
+      int splits = std::min(std::min(sm_count() / row_tiles, kb / 4), lin->fwd_splits_max);
+      GemmArgs t = g;
+      t.n_pairs = np, t.C = lin->partial_fwd, t.ldc = ld_out, t.epi = EPI_STORE;
+      if (splits >= 2 && tc_supported(t)) {
+        const int kb_per = (kb + splits - 1) / splits;
+        t.k_per_split = kb_per * 32, t.split_k = (kb + kb_per - 1) / kb_per;
+        t.skip = skip;
+        int rc = launch_gemm_tc(t, stream);
+        if (rc) return rc;
+        lin->fwd_splits = t.split_k;
+        lin->fwd_bias = (L.has_bias && L.b_off >= 0) ? v + L.b_off : nullptr;
+        cur = dst;
+        which ^= 1;
+        continue;
+      }
+    }
     if (np == 0) {
       // a frozen layer fed by a zero tangent contributes only its (frozen) nothing: R{z} = 0
       HF_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * lin->N * ld_out, stream));
@@ -362,6 +405,8 @@ static int apply_loss_hessian(hf_lin* lin, float* rz, const int32_t* skip, cudaS
   h.N = lin->N, h.C = net->classes, h.ld = pad4(net->classes), h.loss = net->loss, h.final_act = net->L.back().act;
   h.scale = loss_scale(net, lin->n_total);
   h.skip = skip;
+  h.part = lin->fwd_splits > 0 ? lin->partial_fwd : nullptr;
+  h.splits = lin->fwd_splits, h.part_stride = lin->N * (int64_t)pad4(net->classes), h.bias = lin->fwd_bias;
   int64_t blocks = (lin->N + 7) / 8;
   if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
   loss_hessian_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h);
@@ -376,17 +421,22 @@ enum BackMode { BACK_GRADIENT, BACK_GGN, BACK_FISHER, BACK_HESSIAN };
 //   GGN:      out (+)= J^T top
 //   FISHER:   out (+)= scale * sum_n (per-sample gradient)^2
 //   HESSIAN:  top = R{delta_L}; adds the delta_l^T R{a_{l-1}} and delta_l V_l terms and the act'' term
-static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const float* top, int top_buf, float* out,
-                          int accumulate, BackMode mode, const int32_t* skip, cudaStream_t stream) {
+static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const float* top, float* out, int accumulate,
+                          BackMode mode, const int32_t* skip, cudaStream_t stream) {
   const hf_net* net = lin->net;
   const int nl = (int)net->L.size();
   const bool keep = mode == BACK_GRADIENT && (lin->flags & HF_LIN_HESSIAN);
   const int square = mode == BACK_FISHER;
   float scale = 1.f;
   if (mode == BACK_FISHER && net->reduction == HF_RED_MEAN) scale = (float)lin->n_total;
+  // The sweep is a chain of data products (cot[l] -> cot[l-1]) on the caller's stream; the parameter gradients of
+  // layer l only need cot[l], so they run on the side stream while the chain moves on.  Every cotangent has its
+  // own buffer, so there is no write-after-read hazard between the two streams.
+  const bool fork = lin->side != nullptr;
+  cudaStream_t gstream = fork ? lin->side : stream;
   const float* cur = top;
-  int cur_col_tiles = 0;  // > 0: the kernel that produced `cur` also left its column sums in lin->colbuf
-  int which = top_buf >= 0 ? (top_buf ^ 1) : 0;  // next free ping-pong buffer
+  int cur_col_tiles = 0;  // > 0: the kernel that produced `cur` also left its column sums in colbuf[l]
+  if (fork) HF_CUDA(cudaEventRecord(lin->ev[nl - 1], stream));
   for (int l = nl - 1; l >= net->first_trainable; --l) {
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
@@ -399,8 +449,10 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
         A[np] = op_mnc(lin->delta[l], ld_out), B[np] = op_mnc(lin->ra[l - 1], ld_in), ++np;
       }
       const bool has_b = L.has_bias && L.b_off >= 0;
+      if (fork) HF_CUDA(cudaStreamWaitEvent(gstream, lin->ev[l], 0));
       int rc = layer_gradient(lin, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
-                              cur_col_tiles, has_b ? out + L.b_off : nullptr, scale, accumulate, skip, stream);
+                              cur_col_tiles, lin->colbuf[l], has_b ? out + L.b_off : nullptr, scale, accumulate, skip,
+                              gstream);
       if (rc) return rc;
     }
     cur_col_tiles = 0;
@@ -414,7 +466,7 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
         g.A[np] = op_kc(lin->delta[l], ld_out), g.B[np] = op_mnc(v + L.w_off, L.in), ++np;
       }
       g.n_pairs = np;
-      float* dst = keep ? lin->delta[l - 1] : lin->buf[which];
+      float* dst = keep ? lin->delta[l - 1] : lin->cot[l - 1];
       g.C = dst, g.ldc = ld_in;
       g.act = Lp.act;
       g.aux = lin->a[l - 1], g.ldaux = ld_in;
@@ -427,15 +479,19 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       }
       g.skip = skip;
       const int row_tiles = (int)((lin->N + 127) / 128);
-      const bool want_cols = !square && Lp.has_bias && Lp.b_off >= 0 && (size_t)row_tiles * L.in <= lin->colbuf_floats;
-      g.colpart = want_cols ? lin->colbuf : nullptr;
+      const bool want_cols = !square && Lp.has_bias && Lp.b_off >= 0 && (size_t)row_tiles <= lin->col_rows;
+      g.colpart = want_cols ? lin->colbuf[l - 1] : nullptr;
       bool on_tensor = false;
       int rc = run_gemm(net, g, stream, &on_tensor);
       if (rc) return rc;
+      if (fork) HF_CUDA(cudaEventRecord(lin->ev[l - 1], stream));
       cur_col_tiles = (want_cols && on_tensor) ? row_tiles : 0;
       cur = dst;
-      if (!keep) which ^= 1;
     }
+  }
+  if (fork) {
+    HF_CUDA(cudaEventRecord(lin->join, gstream));
+    HF_CUDA(cudaStreamWaitEvent(stream, lin->join, 0));
   }
   return HF_OK;
 }
@@ -492,6 +548,14 @@ int hf_net_set_engine(hf_net_t* net, int32_t engine) {
   return HF_OK;
 }
 
+static void release_async(hf_lin* lin) {
+  for (cudaEvent_t e : lin->ev)
+    if (e) cudaEventDestroy(e);
+  lin->ev.clear();
+  if (lin->join) cudaEventDestroy(lin->join), lin->join = nullptr;
+  if (lin->side) cudaStreamDestroy(lin->side), lin->side = nullptr;
+}
+
 // one pass over the carve-up: either measures (base == nullptr) or assigns pointers
 static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin* lin) {
   size_t off = 0;
@@ -537,8 +601,17 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       pf = std::max(pf, (size_t)colsum_plan(N) * L.out);
     }
   float* part = pf ? (float*)take(sizeof(float) * pf) : nullptr;
-  const size_t cf = loss_only ? 0 : (size_t)std::max<int64_t>(colsum_plan(N), (N + 127) / 128) * net->max_width;
-  float* colb = cf ? (float*)take(sizeof(float) * cf) : nullptr;
+  const int fwd_max = (!loss_only && net->classes <= 32) ? 16 : 0;
+  float* pfwd = fwd_max ? (float*)take(sizeof(float) * fwd_max * N * pad4(net->classes)) : nullptr;
+  if (lin) lin->partial_fwd = pfwd, lin->fwd_splits_max = fwd_max, lin->fwd_splits = 0, lin->fwd_bias = nullptr;
+  const size_t col_rows = (size_t)std::max<int64_t>(colsum_plan(N), (N + 127) / 128);
+  if (lin) lin->cot.assign(nl, nullptr), lin->colbuf.assign(nl, nullptr), lin->col_rows = col_rows;
+  if (!loss_only)
+    for (int l = net->first_trainable; l < nl; ++l) {
+      float* cb = (float*)take(sizeof(float) * col_rows * net->L[l].out);
+      float* ct = l < nl - 1 ? (float*)take(sizeof(float) * N * pad4(net->L[l].out)) : nullptr;
+      if (lin) lin->colbuf[l] = cb, lin->cot[l] = ct;
+    }
   int64_t lb = (N + 7) / 8;
   if (lb > 1024) lb = 1024;
   double* lp = (double*)take(sizeof(double) * lb);
@@ -555,7 +628,6 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   }
   if (lin) {
     lin->prob = prob, lin->deltaL = dL, lin->buf[0] = b0, lin->buf[1] = b1;
-    lin->colbuf = colb, lin->colbuf_floats = cf;
     lin->partial = part, lin->partial_floats = pf, lin->loss_partial = lp, lin->loss_blocks = (int)lb;
   }
   return off;
@@ -580,11 +652,28 @@ int hf_lin_create(const hf_net_t* net, int64_t batch, int32_t flags, void* d_wor
   lin->net = net, lin->N = batch, lin->flags = flags, lin->x = nullptr, lin->n_total = batch;
   lin->have_forward = lin->have_gradient = false;
   carve(net, batch, flags, static_cast<char*>(d_workspace), lin);
+  lin->side = nullptr, lin->join = nullptr;
+  if (!(flags & HF_LIN_LOSS_ONLY) && !getenv("HF_SINGLE_STREAM")) {
+    // side stream + events for the forked gradient work; failure to create them only disables the overlap
+    const int nl = (int)net->L.size();
+    bool ok = cudaStreamCreateWithFlags(&lin->side, cudaStreamNonBlocking) == cudaSuccess;
+    lin->ev.assign(nl, nullptr);
+    for (int l = 0; ok && l < nl; ++l) ok = cudaEventCreateWithFlags(&lin->ev[l], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&lin->join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      release_async(lin);
+      (void)cudaGetLastError();
+    }
+  }
   *out = lin;
   return HF_OK;
 }
 
-void hf_lin_destroy(hf_lin_t* lin) { delete lin; }
+void hf_lin_destroy(hf_lin_t* lin) {
+  if (!lin) return;
+  release_async(lin);
+  delete lin;
+}
 
 const float* hf_lin_logits(const hf_lin_t* lin) { return lin ? lin->a.back() : nullptr; }
 
@@ -636,7 +725,7 @@ int hf_lin_gradient(hf_lin_t* lin, const float* d_theta, float* d_grad, int32_t 
   int rc = check_ready(lin, "hf_lin_gradient", false);
   if (rc) return rc;
   HF_REQUIRE(d_grad, HF_ERR_INVALID, "hf_lin_gradient: null output");
-  rc = backward_sweep(lin, d_theta, nullptr, lin->deltaL, -1, d_grad, accumulate, BACK_GRADIENT, nullptr,
+  rc = backward_sweep(lin, d_theta, nullptr, lin->deltaL, d_grad, accumulate, BACK_GRADIENT, nullptr,
                       (cudaStream_t)stream);
   if (rc == HF_OK) lin->have_gradient = true;
   return rc;
@@ -653,7 +742,7 @@ int hf_ggn_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* 
   if (rc) return rc;
   rc = apply_loss_hessian(lin, lin->buf[top], d_skip, stream);
   if (rc) return rc;
-  return backward_sweep(lin, d_theta, d_v, lin->buf[top], top, d_out, accumulate, BACK_GGN, d_skip, stream);
+  return backward_sweep(lin, d_theta, d_v, lin->buf[top], d_out, accumulate, BACK_GGN, d_skip, stream);
 }
 
 int hf_hessian_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* d_out, int32_t accumulate,
@@ -668,14 +757,14 @@ int hf_hessian_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, flo
   if (rc) return rc;
   rc = apply_loss_hessian(lin, lin->buf[top], d_skip, stream);
   if (rc) return rc;
-  return backward_sweep(lin, d_theta, d_v, lin->buf[top], top, d_out, accumulate, BACK_HESSIAN, d_skip, stream);
+  return backward_sweep(lin, d_theta, d_v, lin->buf[top], d_out, accumulate, BACK_HESSIAN, d_skip, stream);
 }
 
 int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t accumulate, void* stream) {
   int rc = check_ready(lin, "hf_fisher_diag", false);
   if (rc) return rc;
   HF_REQUIRE(d_out, HF_ERR_INVALID, "hf_fisher_diag: null output");
-  return backward_sweep(lin, d_theta, nullptr, lin->deltaL, -1, d_out, accumulate, BACK_FISHER, nullptr,
+  return backward_sweep(lin, d_theta, nullptr, lin->deltaL, d_out, accumulate, BACK_FISHER, nullptr,
                         (cudaStream_t)stream);
 }
 
