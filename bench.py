@@ -261,7 +261,9 @@ def run_native(args):
     pk = peaks()
     roof, extra = None, {}
     if rank == 0:
-        roof, extra = kernel_rooflines(lib, prob, theta, dev, pk, engine)
+        # rank-local problem: the per-kernel timings must not issue collectives the other ranks do not join
+        local_prob = NativeProblem(net, theta, "ggn", [(x, t)], group=None)
+        roof, extra = kernel_rooflines(lib, local_prob, theta, dev, pk, engine)
 
     if rank == 0:
         cpu = None
