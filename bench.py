@@ -304,7 +304,8 @@ def kernel_rooflines(lib, prob, theta, dev, pk, engine):
             flush.fill_(1)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            torch.cuda._sleep(400_000)  # ~0.2 ms of device spin: the host enqueues e0/fn/e1 behind it, so the
+            e0.record()                 # interval holds device time only, not Python launch latency
             fn()
             e1.record()
             torch.cuda.synchronize()

@@ -97,24 +97,47 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
   for (int i = 0; i < NV; ++i) v[i] = scratch[i * 33 + 32];
 }
 
-// After a grid barrier: every CTA sums the per-CTA partials in the same fixed order, so all CTAs
-// (and all ranks, and all runs) see bit-identical scalars.
+// Grid-wide all-reduce of NV doubles for a cooperative (co-resident) launch, fused with the barrier it implies:
+// every CTA publishes {values, generation} in its own 32-byte slot (plain stores + one release store: no atomics, no
+// contended counter), then polls the generation words of all CTAs and sums the values in one fixed order.  Every
+// CTA, every run and every data-parallel rank therefore derives bit-identical scalars.  `gen` must be a value the
+// slot array has not seen since it was zeroed (callers use iteration + 1); each array is used at most once per
+// launch, so a kernel boundary separates consecutive uses.
+struct alignas(32) ReduceSlot {
+  double v[3];
+  unsigned gen;
+  unsigned pad_;
+};
+
 template <int NV>
-__device__ __forceinline__ void grid_sum(const double* partials /*[n_ctas][4]*/, unsigned n_ctas, double (&out)[NV],
-                                         double* scratch) {
+__device__ __forceinline__ void grid_allreduce(ReduceSlot* slots, unsigned n_ctas, unsigned gen, double (&v)[NV],
+                                               double* scratch) {
+  static_assert(NV <= 3, "slot holds three values");
+  block_sum<NV>(v, scratch);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    ReduceSlot* mine = slots + blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) mine->v[i] = v[i];
+    __threadfence();
+    st_release_u32(&mine->gen, gen);
+  }
   if (warp == 0) {
+    for (unsigned c = lane; c < n_ctas; c += 32)
+      while (ld_acquire_u32(&slots[c].gen) != gen) {
+      }
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       double t = 0.0;
-      for (unsigned c = lane; c < n_ctas; c += 32) t += __ldcg(partials + 4 * c + i);
+      for (unsigned c = lane; c < n_ctas; c += 32) t += __ldcg(&slots[c].v[i]);
       t = warp_sum(t);
       if (lane == 0) scratch[i] = t;
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < NV; ++i) out[i] = scratch[i];
+  for (int i = 0; i < NV; ++i) v[i] = scratch[i];
   __syncthreads();
 }
 

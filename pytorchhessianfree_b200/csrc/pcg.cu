@@ -19,11 +19,11 @@ namespace hf {
 
 struct PcgState {
   hf_pcg_status st;
-  unsigned bar[2];
   int32_t first_beta;  // split-mode init done, p = -y still pending
   int32_t martens;
   int64_t max_iter;
-  double partials[2][kMaxCtas][4];
+  // grid all-reduce slots: [0] p.Ap  [1] r.r,(r-b).x,r.y  [2] r.y of a BETA-only launch  [3] start-up sums
+  ReduceSlot slots[4][kMaxCtas];
   double m_iters[2];  // really max_iter + 2 entries
 };
 
@@ -72,15 +72,17 @@ struct IterArgs {
   int64_t P;
   int64_t groups_per_cta;
   PcgState* state;
-  const T* Bp;
-  const T* b;
-  const T* minv;
-  const T* y_ext;
-  T* x;
-  T* r;
-  T* p;
-  T* snapshot;
-  float* p_lo;
+  // distinct vectors (y_ext may equal r, but then neither is written): lets loads of the next group be issued
+  // before the stores of the current one
+  const T* __restrict__ Bp;
+  const T* __restrict__ b;
+  const T* __restrict__ minv;
+  const T* __restrict__ y_ext;
+  T* __restrict__ x;
+  T* __restrict__ r;
+  T* __restrict__ p;
+  T* __restrict__ snapshot;
+  float* __restrict__ p_lo;
   double lambda;
   int phase;
   int resident;
@@ -137,11 +139,13 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
   const double ry_old = s->st.ry;
   const int iter = s->st.iter + 1;
   const bool first_beta = s->first_beta != 0;
+  const unsigned gen = (unsigned)iter + (first_beta ? 0u : 1u);  // fresh for every use of a slot array
   double ry_new = 0.0;
 
   if (a.phase & HF_PCG_ALPHA) {
     // ---- phase 1: Ap = Bp + lambda p, partial p.Ap ------------------------------------------------
     T acc = T(0);
+#pragma unroll 2
     for (int j = threadIdx.x; j < nloc; j += kThreads) {
       const V p4 = load_vec(a.p, g0 + j, a.P);
       V q4 = load_vec(a.Bp, g0 + j, a.P);
@@ -156,10 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
       }
     }
     double red1[1] = {(double)acc};
-    block_sum<1>(red1, scratch);
-    if (threadIdx.x == 0) s->partials[0][blockIdx.x][0] = red1[0];
-    grid_barrier(s->bar, n_ctas);
-    grid_sum<1>(&s->partials[0][0][0], n_ctas, red1, scratch);
+    grid_allreduce<1>(s->slots[0], n_ctas, gen, red1, scratch);
     const double pAp = red1[0];
     const double alpha = ry_old / pAp;
     const T al = (T)alpha;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
     // ---- phase 2: x += alpha p, r += alpha Ap, y = M r, partial r.r, (r-b).x, r.y ------------------
     const bool want_y = (a.phase & HF_PCG_BETA) != 0;
     T acc_rr = T(0), acc_m = T(0), acc_ry = T(0);
+#pragma unroll 2
     for (int j = threadIdx.x; j < nloc; j += kThreads) {
       V p4, q4;
       if (a.resident) {
@@ -203,14 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
       }
     }
     double red3[3] = {(double)acc_rr, (double)acc_m, (double)acc_ry};
-    block_sum<3>(red3, scratch);
-    if (threadIdx.x == 0) {
-      s->partials[1][blockIdx.x][0] = red3[0];
-      s->partials[1][blockIdx.x][1] = red3[1];
-      s->partials[1][blockIdx.x][2] = red3[2];
-    }
-    grid_barrier(s->bar, n_ctas);
-    grid_sum<3>(&s->partials[1][0][0], n_ctas, red3, scratch);
+    grid_allreduce<3>(s->slots[1], n_ctas, gen, red3, scratch);
     ry_new = red3[2];
     double m_new, rnorm;
     const int reason = terminate_cg<T>(s, iter, red3[0], red3[1], writer, &m_new, &rnorm);
@@ -245,13 +240,9 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
       if (a.resident) sq[j] = y4;
     }
     double red1[1] = {(double)acc_ry};
-    block_sum<1>(red1, scratch);
-    if (threadIdx.x == 0) s->partials[1][blockIdx.x][2] = red1[0];
-    grid_barrier(s->bar, n_ctas);
-    // same slot and same summation order as the fused launch
-    double red3[3];
-    grid_sum<3>(&s->partials[1][0][0], n_ctas, red3, scratch);
-    ry_new = red3[2];
+    // same per-thread order, same block and grid summation order as the fused launch -> same bits
+    grid_allreduce<1>(s->slots[2], n_ctas, gen, red1, scratch);
+    ry_new = red1[0];
   }
 
   // ---- phase 3: beta = ry'/ry, p = -y + beta p -----------------------------------------------------
@@ -365,16 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_init_kernel(InitArgs<T> a) {
     }
   }
   double red[3] = {(double)acc_bb, (double)acc_m, (double)acc_ry};
-  block_sum<3>(red, scratch);
-  if (threadIdx.x == 0) {
-    s->partials[1][blockIdx.x][0] = red[0];
-    s->partials[1][blockIdx.x][1] = red[1];
-    s->partials[1][blockIdx.x][2] = red[2];
-  }
-  grid_barrier(s->bar, n_ctas);
-  if (blockIdx.x != 0) return;
-  grid_sum<3>(&s->partials[1][0][0], n_ctas, red, scratch);
-  if (threadIdx.x == 0) {
+  grid_allreduce<3>(s->slots[3], n_ctas, 1u, red, scratch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     const T bnorm = (T)sqrt(red[0]);
     double bound = a.tol * (double)bnorm;
     if (a.atol >= 0.0) bound = fmax(bound, a.atol);
@@ -520,8 +503,8 @@ int hf_pcg_init(int dtype, int64_t P, void* d_state, size_t state_bytes, const v
   HF_REQUIRE(aligned16(d_state) && aligned16(d_b) && aligned16(d_x) && aligned16(d_r) && aligned16(d_p) &&
                  aligned16(d_Bx0) && aligned16(d_x0) && aligned16(d_minv),
              HF_ERR_INVALID, "hf_pcg_init: all vectors must be 16-byte aligned");
-  // the barrier words must start from zero; everything else is written by the kernel
-  HF_CUDA(cudaMemsetAsync(static_cast<char*>(d_state) + offsetof(PcgState, bar), 0, 2 * sizeof(unsigned),
+  // the generation words of the reduce slots must start from zero; everything else is written by the kernel
+  HF_CUDA(cudaMemsetAsync(static_cast<char*>(d_state) + offsetof(PcgState, slots), 0, sizeof(ReduceSlot) * 4 * kMaxCtas,
                           (cudaStream_t)stream));
   if (dtype == HF_F32)
     return launch_init<float>(P, d_state, d_Bx0, d_x0, d_b, d_minv, lambda, tol, atol, max_iter, martens, split, d_x,
