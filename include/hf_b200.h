@@ -70,6 +70,9 @@ const char* hf_last_error_string(void);
 int hf_device_sm_count(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long hf_debug_launch_count(void);
+/* profiling aid: if d_buf (>= 8 * 256 uint64) is non-NULL, hf_pcg_iter records %globaltimer at its phase boundaries
+ * per CTA: [cta][0] start, [1] partial p.Ap ready, [2] alpha known, [3] x/r updated, [4] beta known, [5] p written */
+int hf_debug_pcg_trace(void* d_buf);
 
 /* ------------------------------------------------------------------------------------------
  * Fused PCG vector pass  (cg.py:186-224 + optimizer.py:266 + preconditioners.py:125)

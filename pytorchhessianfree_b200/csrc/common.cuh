@@ -97,17 +97,25 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
   for (int i = 0; i < NV; ++i) v[i] = scratch[i * 33 + 32];
 }
 
-// Grid-wide all-reduce of NV doubles for a cooperative (co-resident) launch, fused with the barrier it implies:
-// every CTA publishes {values, generation} in its own 32-byte slot (plain stores + one release store: no atomics, no
-// contended counter), then polls the generation words of all CTAs and sums the values in one fixed order.  Every
-// CTA, every run and every data-parallel rank therefore derives bit-identical scalars.  `gen` must be a value the
-// slot array has not seen since it was zeroed (callers use iteration + 1); each array is used at most once per
-// launch, so a kernel boundary separates consecutive uses.
-struct alignas(32) ReduceSlot {
-  double v[3];
-  unsigned gen;
-  unsigned pad_;
+// Grid-wide all-reduce of NV doubles for a cooperative (co-resident) launch, fused with the barrier it implies.
+// Low-latency flag-in-data protocol: every 64-bit word a CTA publishes carries 32 payload bits and the 32-bit
+// generation, so a reader that sees the right generation has the payload too -- one store, one poll round trip, no
+// fences, no atomics, no contended counter.  Each of the first kMaxCtas/32 warps polls 32 CTAs, the per-warp sums are
+// combined in a fixed order, so every CTA, every run and every data-parallel rank derives bit-identical scalars.
+// `gen` must be a value the slot array has not seen since it was zeroed (callers use iteration + 1); each array is
+// used at most once per launch, so a kernel boundary separates consecutive uses.
+struct alignas(64) ReduceSlot {
+  unsigned long long w[8];  // w[2i] = {low 32 bits of value i, gen}, w[2i+1] = {high 32 bits of value i, gen}
 };
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 template <int NV>
 __device__ __forceinline__ void grid_allreduce(ReduceSlot* slots, unsigned n_ctas, unsigned gen, double (&v)[NV],
@@ -118,26 +126,47 @@ __device__ __forceinline__ void grid_allreduce(ReduceSlot* slots, unsigned n_cta
   if (threadIdx.x == 0) {
     ReduceSlot* mine = slots + blockIdx.x;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) mine->v[i] = v[i];
-    __threadfence();
-    st_release_u32(&mine->gen, gen);
+    for (int i = 0; i < NV; ++i) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(v[i]);
+      st_relaxed_u64(&mine->w[2 * i], ((unsigned long long)gen << 32) | (bits & 0xffffffffull));
+      st_relaxed_u64(&mine->w[2 * i + 1], ((unsigned long long)gen << 32) | (bits >> 32));
+    }
   }
-  if (warp == 0) {
-    for (unsigned c = lane; c < n_ctas; c += 32)
-      while (ld_acquire_u32(&slots[c].gen) != gen) {
-      }
-    __syncwarp();
+  double* wsum = scratch + 100;  // [kMaxCtas/32][3], clear of block_sum's area
+  if (warp < kMaxCtas / 32) {
+    const unsigned c = warp * 32 + lane;
+    double t[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) t[i] = 0.0;
+    if (c < n_ctas) {
+      unsigned long long w[2 * NV];
+      bool ready;
+      do {
+        ready = true;
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) {
+          w[j] = ld_relaxed_u64(&slots[c].w[j]);
+          ready = ready && ((unsigned)(w[j] >> 32) == gen);
+        }
+      } while (!ready);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        t[i] = __longlong_as_double((long long)((w[2 * i] & 0xffffffffull) | (w[2 * i + 1] << 32)));
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      double t = 0.0;
-      for (unsigned c = lane; c < n_ctas; c += 32) t += __ldcg(&slots[c].v[i]);
-      t = warp_sum(t);
-      if (lane == 0) scratch[i] = t;
+      t[i] = warp_sum(t[i]);
+      if (lane == 0) wsum[warp * 3 + i] = t[i];
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = scratch[i];
+  for (int i = 0; i < NV; ++i) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMaxCtas / 32; ++w) t += wsum[w * 3 + i];
+    v[i] = t;
+  }
   __syncthreads();
 }
 

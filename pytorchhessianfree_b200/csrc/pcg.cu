@@ -28,6 +28,16 @@ struct PcgState {
 };
 
 constexpr int kThreads = 1024;
+
+// optional phase trace (tools/pcg_trace.py): per CTA, %globaltimer at the phase boundaries of pcg_iter_kernel
+__device__ unsigned long long* g_pcg_trace = nullptr;
+__device__ __forceinline__ void trace_mark(int slot) {
+  if (g_pcg_trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_pcg_trace[blockIdx.x * 8 + slot] = t;
+  }
+}
 constexpr size_t kResidentBytes = 200 * 1024;  // dynamic smem budget for the resident p / Ap slices
 
 template <typename T>
@@ -142,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
   const unsigned gen = (unsigned)iter + (first_beta ? 0u : 1u);  // fresh for every use of a slot array
   double ry_new = 0.0;
 
+  trace_mark(0);
   if (a.phase & HF_PCG_ALPHA) {
     // ---- phase 1: Ap = Bp + lambda p, partial p.Ap ------------------------------------------------
     T acc = T(0);
@@ -160,7 +171,9 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
       }
     }
     double red1[1] = {(double)acc};
+    trace_mark(1);
     grid_allreduce<1>(s->slots[0], n_ctas, gen, red1, scratch);
+    trace_mark(2);
     const double pAp = red1[0];
     const double alpha = ry_old / pAp;
     const T al = (T)alpha;
@@ -205,7 +218,9 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
       }
     }
     double red3[3] = {(double)acc_rr, (double)acc_m, (double)acc_ry};
+    trace_mark(3);
     grid_allreduce<3>(s->slots[1], n_ctas, gen, red3, scratch);
+    trace_mark(4);
     ry_new = red3[2];
     double m_new, rnorm;
     const int reason = terminate_cg<T>(s, iter, red3[0], red3[1], writer, &m_new, &rnorm);
@@ -284,6 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
       }
     }
   }
+  trace_mark(5);
   if (writer) {
     s->st.ry = ry_new;
     s->st.beta = beta;
@@ -491,6 +507,12 @@ size_t hf_pcg_state_bytes(int64_t max_iter) {
 }
 
 size_t hf_pcg_m_iters_offset(void) { return offsetof(PcgState, m_iters); }
+
+int hf_debug_pcg_trace(void* d_buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(d_buf);
+  HF_CUDA(cudaMemcpyToSymbol(g_pcg_trace, &p, sizeof(p)));
+  return HF_OK;
+}
 
 int hf_pcg_init(int dtype, int64_t P, void* d_state, size_t state_bytes, const void* d_Bx0, const void* d_x0,
                 const void* d_b, const void* d_minv, double lambda, double tol, double atol, int64_t max_iter,
