@@ -73,6 +73,9 @@ long long hf_debug_launch_count(void);
 /* profiling aid: if d_buf (>= 8 * 256 uint64) is non-NULL, hf_pcg_iter records %globaltimer at its phase boundaries
  * per CTA: [cta][0] start, [1] partial p.Ap ready, [2] alpha known, [3] x/r updated, [4] beta known, [5] p written */
 int hf_debug_pcg_trace(void* d_buf);
+/* same for the tcgen05 contraction kernel: [cta][0] entry, [1] prologue done (barriers, TMEM), [2] first stage landed,
+ * [3] accumulator complete, [4] epilogue done (d_buf >= 8 * n_ctas uint64) */
+int hf_debug_tc_trace(void* d_buf);
 
 /* ------------------------------------------------------------------------------------------
  * Fused PCG vector pass  (cg.py:186-224 + optimizer.py:266 + preconditioners.py:125)

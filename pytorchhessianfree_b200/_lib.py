@@ -59,6 +59,7 @@ SIGNATURES = {
     "hf_device_sm_count": (C.c_int, []),
     "hf_debug_launch_count": (C.c_longlong, []),
     "hf_debug_pcg_trace": (C.c_int, [_vp]),
+    "hf_debug_tc_trace": (C.c_int, [_vp]),
     "hf_pcg_state_bytes": (_sz, [_i64]),
     "hf_pcg_m_iters_offset": (_sz, []),
     "hf_pcg_init": (C.c_int, [C.c_int, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _i64, C.c_int, C.c_int,

@@ -29,6 +29,17 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;               // rawA | rawB | loA |
 constexpr int TC_THREADS = 192;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
+// optional phase trace (tools/tc_trace.py): per CTA, %globaltimer at [0] entry [1] prologue done [2] first stage landed
+// [3] accumulator complete [4] epilogue done
+__device__ unsigned long long* g_tc_trace = nullptr;
+__device__ __forceinline__ void tc_mark(int slot, bool who) {
+  if (g_tc_trace && who) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_tc_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+  }
+}
+
 struct TcArgs {
   GemmArgs g;
   int a_mn[2], b_mn[2];  // 1 = operand is MN-contiguous in global memory (MN-major UMMA operand)
@@ -108,9 +119,167 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int mn_major, in
   return mn_major ? smem_desc(base + ks * 1024, BKT * 128, 512, 1) : smem_desc(base + ks * 32, 16, 1024, 2);
 }
 
+// ---- fused epilogue, one specialisation per (epilogue kind, activation): the row loop is straight-line vector code
+// (with one warp per scheduler every branch and dependent ALU op is exposed latency, so nothing is decided per element)
+template <int ACT>
+__device__ __forceinline__ float d1(float s) {
+  if (ACT == HF_ACT_RELU) return s > 0.f ? 1.f : 0.f;
+  if (ACT == HF_ACT_SIGMOID) return s * (1.f - s);
+  if (ACT == HF_ACT_TANH) return 1.f - s * s;
+  return 1.f;
+}
+template <int ACT>
+__device__ __forceinline__ float d2(float s) {
+  if (ACT == HF_ACT_SIGMOID) return s * (1.f - s) * (1.f - 2.f * s);
+  if (ACT == HF_ACT_TANH) return -2.f * s * (1.f - s * s);
+  return 0.f;
+}
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float z) {
+  if (ACT == HF_ACT_RELU) return z > 0.f ? z : 0.f;
+  if (ACT == HF_ACT_SIGMOID) return 1.f / (1.f + expf(-z));
+  if (ACT == HF_ACT_TANH) return tanhf(z);
+  return z;
+}
+
+template <bool VEC>
+__device__ __forceinline__ void ld4(const float* p, int cnt, float (&o)[4]) {
+  if (VEC) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    o[0] = t.x, o[1] = t.y, o[2] = t.z, o[3] = t.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = e < cnt ? p[e] : 0.f;
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void st4(float* p, int cnt, const float (&o)[4]) {
+  if (VEC) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (e < cnt) p[e] = o[e];
+  }
+}
+
+// rows [m_base, m_base+32) x columns [n, n+4) of the tile; `stage` holds the warp's 32 accumulator rows
+template <int EPI, int ACT, bool VEC>
+__device__ __forceinline__ void epilogue_rows(const GemmArgs& g, const float* stage, int m_base, int n, int lane, int cnt,
+                                              float (&cs)[4]) {
+  constexpr int LDS_ROW = BN + 4;
+  constexpr bool NEED_AUX = ACT != HF_ACT_NONE && EPI >= EPI_BIAS_DACT;
+  // Every field is copied into a register first: `g` lives in the kernel-parameter window and is read through a
+  // generic pointer, which the compiler must otherwise re-load after every global store (possible aliasing).
+  const int64_t ldc = g.ldc, ldaux = g.ldaux;
+  float* const C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0) + n;
+  float* const C2 = g.C2 ? g.C2 + n : nullptr;
+  const float* const aux = g.aux ? g.aux + n : nullptr;
+  const float* const hga = g.h_ga ? g.h_ga + n : nullptr;
+  const float* const hrz = g.h_rz ? g.h_rz + n : nullptr;
+  const float alpha = g.alpha;
+  const int rows = min(32, g.M - m_base);
+  float bi[4] = {0.f, 0.f, 0.f, 0.f};
+  if ((EPI == EPI_STORE || EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_DACT) && g.bias) ld4<VEC>(g.bias + n, cnt, bi);
+  constexpr int RB = 4;  // rows in flight: their global loads are all issued before the first use
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // column sums in registers (`cs` is memory: it crosses a call boundary)
+#pragma unroll 1
+  for (int r0 = 0; r0 < rows; r0 += RB) {
+    float x[RB][4], au[RB][4], ga[RB][4], rz[RB][4];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+      const int r = min(r0 + j, rows - 1);  // clamp: tail slots re-read the last row and are not stored
+      const int64_t m = m_base + r;
+      const float4 t = *reinterpret_cast<const float4*>(stage + r * LDS_ROW + lane * 4);
+      x[j][0] = t.x, x[j][1] = t.y, x[j][2] = t.z, x[j][3] = t.w;
+      if (NEED_AUX) ld4<VEC>(aux + m * ldaux, cnt, au[j]);
+      if (EPI == EPI_DACT_H && hga) {
+        ld4<VEC>(hga + m * ldaux, cnt, ga[j]);
+        ld4<VEC>(hrz + m * ldaux, cnt, rz[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+      if (r0 + j >= rows) break;
+      const int64_t m = m_base + r0 + j;
+      if (EPI == EPI_STORE) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[j][e] = alpha * x[j][e] + bi[e];
+      } else if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[j][e] = act_fwd<ACT>(x[j][e] + bi[e]);
+      } else if (EPI == EPI_BIAS_DACT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[j][e] += bi[e];
+        if (C2) st4<VEC>(C2 + m * ldc, cnt, x[j]);
+        if (NEED_AUX)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[j][e] *= d1<ACT>(au[j][e]);
+      } else if (EPI == EPI_DACT) {
+        if (C2) st4<VEC>(C2 + m * ldc, cnt, x[j]);
+        if (NEED_AUX)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[j][e] *= d1<ACT>(au[j][e]);
+      } else {  // EPI_DACT_H
+        if (NEED_AUX) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[j][e] *= d1<ACT>(au[j][e]);
+          if (hga)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[j][e] += ga[j][e] * d2<ACT>(au[j][e]) * rz[j][e];
+        }
+      }
+      st4<VEC>(C + m * ldc, cnt, x[j]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] += x[j][e];
+    }
+    if (r0 == 0) tc_mark(6, threadIdx.x == 0);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) cs[e] = acc[e];
+  tc_mark(7, threadIdx.x == 0);
+}
+
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_vec(const GemmArgs& g, const float* stage, int m_base, int n, int lane,
+                                             float (&cs)[4]) {
+  const int cnt = min(4, g.N - n);
+  if (cnt <= 0 || m_base >= g.M) return;
+  float* C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(g.C2) | reinterpret_cast<uintptr_t>(g.aux) |
+                      reinterpret_cast<uintptr_t>(g.h_ga) | reinterpret_cast<uintptr_t>(g.h_rz) |
+                      reinterpret_cast<uintptr_t>(g.bias)) & 15u) == 0 && g.ldc % 4 == 0 && g.ldaux % 4 == 0;
+  if (al16 && cnt == 4)
+    epilogue_rows<EPI, ACT, true>(g, stage, m_base, n, lane, cnt, cs);
+  else
+    epilogue_rows<EPI, ACT, false>(g, stage, m_base, n, lane, cnt, cs);
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_act(const GemmArgs& g, const float* stage, int m_base, int n, int lane,
+                                             float (&cs)[4]) {
+  switch (g.act) {
+    case HF_ACT_RELU: epilogue_vec<EPI, HF_ACT_RELU>(g, stage, m_base, n, lane, cs); break;
+    case HF_ACT_SIGMOID: epilogue_vec<EPI, HF_ACT_SIGMOID>(g, stage, m_base, n, lane, cs); break;
+    case HF_ACT_TANH: epilogue_vec<EPI, HF_ACT_TANH>(g, stage, m_base, n, lane, cs); break;
+    default: epilogue_vec<EPI, HF_ACT_NONE>(g, stage, m_base, n, lane, cs); break;
+  }
+}
+
+__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const float* stage, int m_base, int n, int lane,
+                                               float (&cs)[4]) {
+  switch (g.epi) {
+    case EPI_STORE: epilogue_vec<EPI_STORE, HF_ACT_NONE>(g, stage, m_base, n, lane, cs); break;
+    case EPI_BIAS_ACT: epilogue_act<EPI_BIAS_ACT>(g, stage, m_base, n, lane, cs); break;
+    case EPI_BIAS_DACT: epilogue_act<EPI_BIAS_DACT>(g, stage, m_base, n, lane, cs); break;
+    case EPI_DACT: epilogue_act<EPI_DACT>(g, stage, m_base, n, lane, cs); break;
+    default: epilogue_act<EPI_DACT_H>(g, stage, m_base, n, lane, cs); break;
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const TcArgs p) {
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ TcArgs p) {
   const GemmArgs& g = p.g;
   if (g.skip && *g.skip) return;  // uniform: solver already terminated
   extern __shared__ uint8_t smem_dyn[];
@@ -123,6 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tc_mark(0, threadIdx.x == 0);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
@@ -146,6 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  tc_mark(1, threadIdx.x == 0);
 
   if (warp == 4) {
     // ---------------- TMA producer ----------------
@@ -204,6 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int it = 0; it < total; ++it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(&full_raw[s], ph);
+      if (it == 0) tc_mark(2, threadIdx.x == 0);
       const float4* src = reinterpret_cast<const float4*>(tiles + s * STAGE_BYTES);
       float4* dst = reinterpret_cast<float4*>(tiles + s * STAGE_BYTES + 2 * TILE_BYTES);
 #pragma unroll 4
@@ -227,8 +399,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(acc_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    tc_mark(3, threadIdx.x == 0);
     constexpr int LDS_ROW = BN + 4;
     float* stage = reinterpret_cast<float*>(tiles) + warp * 32 * LDS_ROW;
+#pragma unroll 2
     for (int c = 0; c < BN; c += 16) {
       float v[16];
       if (total > 0) {
@@ -242,99 +416,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         *reinterpret_cast<float4*>(stage + lane * LDS_ROW + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
     __syncwarp();
-    float* C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0);
-    const bool al16 = ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(g.C2) | reinterpret_cast<uintptr_t>(g.aux) |
-                        reinterpret_cast<uintptr_t>(g.h_ga) | reinterpret_cast<uintptr_t>(g.h_rz) |
-                        reinterpret_cast<uintptr_t>(g.bias)) & 15u) == 0 && g.ldc % 4 == 0 && g.ldaux % 4 == 0;
-    const int n = n0 + lane * 4;
-    const int cnt = min(4, g.N - n);
-    const bool vec = al16 && cnt == 4;
-    auto load4 = [&](const float* p, float (&o)[4]) {
-      if (vec) {
-        const float4 t = *reinterpret_cast<const float4*>(p);
-        o[0] = t.x, o[1] = t.y, o[2] = t.z, o[3] = t.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = e < cnt ? p[e] : 0.f;
-      }
-    };
-    auto store4 = [&](float* p, const float (&o)[4]) {
-      if (vec) {
-        *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (e < cnt) p[e] = o[e];
-      }
-    };
+    tc_mark(5, threadIdx.x == 0);
     float cs[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of what this lane stores (bias gradient of the next layer)
-    if (cnt > 0) {
-      float bi[4] = {0.f, 0.f, 0.f, 0.f};
-      if (g.bias) load4(g.bias + n, bi);
-      const bool need_aux = g.act != HF_ACT_NONE && g.epi >= EPI_BIAS_DACT;
-      constexpr int RB = 8;  // rows in flight: all their global loads are issued before the first use
-      for (int r0 = 0; r0 < 32; r0 += RB) {
-        float aub[RB][4];
-        if (need_aux) {
-#pragma unroll
-          for (int j = 0; j < RB; ++j) {
-            const int mj = m0 + warp * 32 + r0 + j;
-            if (mj < g.M) load4(g.aux + (int64_t)mj * g.ldaux + n, aub[j]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < RB; ++j) {
-          const int r = r0 + j;
-          const int m = m0 + warp * 32 + r;
-          if (m >= g.M) break;
-          float x[4], au[4] = {0.f, 0.f, 0.f, 0.f};
-          const float4 t = *reinterpret_cast<const float4*>(stage + r * LDS_ROW + lane * 4);
-          x[0] = t.x, x[1] = t.y, x[2] = t.z, x[3] = t.w;
-          if (need_aux) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) au[e] = aub[j][e];
-          }
-          switch (g.epi) {
-            case EPI_STORE:
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = g.alpha * x[e] + bi[e];
-              break;
-            case EPI_BIAS_ACT:
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = act_apply(g.act, x[e] + bi[e]);
-              break;
-            case EPI_BIAS_DACT:
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] += bi[e];
-              if (g.C2) store4(g.C2 + (int64_t)m * g.ldc + n, x);
-              if (need_aux)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
-              break;
-            case EPI_DACT:
-              if (g.C2) store4(g.C2 + (int64_t)m * g.ldc + n, x);
-              if (need_aux)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
-              break;
-            case EPI_DACT_H: {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] *= act_d1(g.act, au[e]);
-              if (g.h_ga) {
-                float ga[4], rz[4];
-                load4(g.h_ga + (int64_t)m * g.ldaux + n, ga);
-                load4(g.h_rz + (int64_t)m * g.ldaux + n, rz);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] += ga[e] * act_d2(g.act, au[e]) * rz[e];
-              }
-            } break;
-          }
-          store4(C + (int64_t)m * g.ldc + n, x);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) cs[e] += x[e];
-        }
-      }
-    }
+    epilogue_dispatch(g, stage, m0 + warp * 32, n0 + lane * 4, lane, cs);
     if (g.colpart) {
       // 4 warps x 32 rows -> one row of column sums per CTA, fixed order (deterministic)
       float* red = reinterpret_cast<float*>(tiles) + 4 * 32 * (BN + 4);
@@ -353,6 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  tc_mark(4, threadIdx.x == 0);
   if (warp == 5) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
   }
@@ -410,6 +495,12 @@ static int make_map(CUtensorMap* map, const Operand& op, int MN, int K) {
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HF_REQUIRE(r == CUDA_SUCCESS, HF_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return HF_OK;
+}
+
+int set_tc_trace(void* d_buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(d_buf);
+  HF_CUDA(cudaMemcpyToSymbol(g_tc_trace, &p, sizeof(p)));
   return HF_OK;
 }
 
