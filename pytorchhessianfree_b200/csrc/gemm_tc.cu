@@ -83,6 +83,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// round to the nearest TF32 value (the MMA unit would otherwise truncate the low word: a bias of ~2^-22 per operand)
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -382,10 +388,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int i = threadIdx.x; i < 2 * TILE_BYTES / 16; i += 128) {
         const float4 v = src[i];
         float4 lo;
-        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        lo.x = tf32_round(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+        lo.y = tf32_round(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+        lo.z = tf32_round(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+        lo.w = tf32_round(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
         dst[i] = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA unit

@@ -241,6 +241,11 @@ static SplitPlan plan_split(int M, int N, int64_t K, bool tensor_tiles) {
   int64_t max_split = ktiles / 4;  // at least 128 samples per split
   if (max_split < 1) max_split = 1;
   if (want > max_split) want = max_split;
+  // The tensor core adds each 8-wide product group into the FP32 accumulator with truncation, a bias that grows
+  // linearly with the number of accumulation steps (measured against float64: 3e-5 relative after 3000 samples,
+  // ~1e-4 after 30 000).  Batch contractions are therefore cut into partial sums of at most 1024 samples, which
+  // the reduction kernel adds in properly rounded FP32.
+  if (tensor_tiles && want < (ktiles + 31) / 32) want = (ktiles + 31) / 32;
   if (want > 64) want = 64;
   if (want < 1) want = 1;
   const int64_t kt_per = (ktiles + want - 1) / want;
@@ -693,7 +698,11 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     g.B[0] = op_kc(weight_ptr(L, d_theta), L.in);
     g.C = lin->a[l], g.ldc = pad4(L.out);
     g.epi = EPI_BIAS_ACT, g.act = L.act, g.bias = bias_ptr(L, d_theta);
-    int rc = run_gemm(net, g, stream);
+    // The linearisation point fixes the ReLU masks for the whole solve, so it is evaluated in plain FP32: the
+    // ~5e-6 error of the 3xTF32 tiles would flip a few dozen of the 4M masks of the MLP config (each flip moves a
+    // gradient row by ~1/sqrt(N)).  Loss-only evaluations (line search, backtracking) have no masks to fix and
+    // stay on the tensor-core tiles.
+    int rc = (lin->flags & HF_LIN_LOSS_ONLY) ? run_gemm(net, g, stream) : launch_gemm_simt(g, stream);
     if (rc) return rc;
   }
   LossArgs a;

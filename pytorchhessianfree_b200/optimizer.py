@@ -349,11 +349,10 @@ class HessianFree(torch.optim.Optimizer):
             group=self.process_group)
         mvp_loss = problem.linearize()
         grad = problem.gradient()
-        if problem.loss_lins is problem.mvp_lins:
+        if loss_datalist is mvp_datalist:
             init_loss = float(mvp_loss.to(torch.float32).item())
         else:
             init_loss = problem.losses_at([torch.zeros_like(theta)])[0]
-            problem.linearize()
         if test_deterministic:
             self._test_mvp_deterministic(problem.mvp)
         return self._newton_step(init_loss, grad, problem, problem.mvp, M_func, None)

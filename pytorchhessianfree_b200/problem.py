@@ -28,7 +28,10 @@ class NativeProblem:
         hess = curvature_opt == "hessian"
         self.mvp_lins: List[Linearization] = [net.linearize(x, t, hessian=hess) for x, t in mvp_data]
         self.grad_lins = self.mvp_lins if grad_data is None else [net.linearize(x, t) for x, t in grad_data]
-        self.loss_lins = self.mvp_lins if loss_data is None else [net.linearize(x, t, loss_only=True) for x, t in loss_data]
+        # candidate losses (line search, backtracking, LM ratio) run on their own loss-only linearisations: two
+        # ping-pong buffers per chunk, tensor-core tiles, and the curvature linearisation stays intact
+        self.loss_lins = [net.linearize(l.x, l.targets, loss_only=True) for l in self.mvp_lins] if loss_data is None \
+            else [net.linearize(x, t, loss_only=True) for x, t in loss_data]
         self.n_mvp, self.n_grad, self.n_loss = (self._count(l) for l in (self.mvp_lins, self.grad_lins, self.loss_lins))
         self._cand = torch.empty_like(theta)
         self._linearized = False
@@ -100,7 +103,6 @@ class NativeProblem:
             for lin in self.loss_lins:
                 lin.forward(self._cand, self.n_loss, acc[k:])
         _all_reduce(acc, self.group)
-        self._linearized = False  # activations now belong to a candidate point
         return acc.to(torch.float32).tolist()
 
     def target_function(self):
