@@ -273,14 +273,32 @@ static __global__ void reduce_partials2_kernel(const float* __restrict__ partW, 
                                                int64_t countB, float* __restrict__ outB, float scale, int accumulate,
                                                const int32_t* __restrict__ skip) {
   if (skip && *skip) return;
-  const int64_t total = countW + countB;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const bool w = i < countW;
-    const int64_t j = w ? i : i - countW;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+  // weight slice, 4 elements per thread: all split loads of a group are independent, so they are in flight together
+  const bool vec = countW % 4 == 0 && ((reinterpret_cast<uintptr_t>(partW) | reinterpret_cast<uintptr_t>(outW)) & 15u) == 0;
+  const int64_t nvec = vec ? countW / 4 : 0;
+  for (int64_t v = tid; v < nvec; v += nthreads) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int z = 0; z < splitsW; ++z) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(partW + (int64_t)z * countW) + v);
+      s.x += t.x, s.y += t.y, s.z += t.z, s.w += t.w;
+    }
+    float4* o = reinterpret_cast<float4*>(outW) + v;
+    float4 r = accumulate ? *o : make_float4(0.f, 0.f, 0.f, 0.f);
+    r.x += scale * s.x, r.y += scale * s.y, r.z += scale * s.z, r.w += scale * s.w;
+    *o = r;
+  }
+  // scalar tail of the weight slice (unaligned case) and the bias slice
+  const int64_t scalar_w = countW - 4 * nvec, total = scalar_w + countB;
+  for (int64_t i = tid; i < total; i += nthreads) {
+    const bool w = i < scalar_w;
+    const int64_t j = w ? 4 * nvec + i : i - scalar_w;
     const float* part = w ? partW : partB;
     const int64_t stride = w ? countW : countB;
     const int splits = w ? splitsW : splitsB;
     float s = 0.f;
+#pragma unroll 8
     for (int z = 0; z < splits; ++z) s += part[(int64_t)z * stride + j];
     float* out = w ? outW : outB;
     out[j] = (accumulate ? out[j] : 0.f) + scale * s;

@@ -322,8 +322,8 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
   }
   const int64_t count_w = out_w ? (int64_t)M * N : 0, count_b = out_b ? M : 0;
   if (count_w + count_b == 0) return HF_OK;
-  int64_t blocks = (count_w + count_b + 255) / 256;
-  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  int64_t blocks = (count_w / 4 + count_b + 255) / 256 + 1;
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
   reduce_partials2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, splits_w, count_w, out_w, colbuf, splits_b,
                                                                count_b, out_b, scale, accumulate, skip);
   HF_LAUNCH_CHECK();
