@@ -317,25 +317,30 @@ def kernel_rooflines(lib, prob, theta, dev, pk, engine):
     v, out = torch.randn_like(theta), torch.empty_like(theta)
     t_mv = timed(lambda: prob.matvec(v, out))
     f_mv = flops_per_product()
-    # dominant contraction: the layer-1 weight-gradient product  G1[512,784] = delta1^T[512,4096] a0[4096,784]
+    # dominant kernel: the tensor-tile contraction.  Timed on the shape that heads the launch list of a product, the
+    # layer-1 R-op forward  Rz1[4096,512] = a0[4096,784] V1[512,784]^T  (128 CTAs = one wave), through the same C entry
+    # point the products use.
     from pytorchhessianfree_b200._lib import Operand
-    d1 = torch.randn(BATCH, 512, device=dev)
     a0 = torch.randn(BATCH, 784, device=dev)
-    c = torch.empty(512, 784, device=dev)
-    A = (Operand * 1)(Operand(d1.data_ptr(), 1, 512))
-    B = (Operand * 1)(Operand(a0.data_ptr(), 1, 784))
+    v1 = torch.randn(512, 784, device=dev)
+    c = torch.empty(BATCH, 512, device=dev)
+    A = (Operand * 1)(Operand(a0.data_ptr(), 784, 1))
+    B = (Operand * 1)(Operand(v1.data_ptr(), 784, 1))
     eng = 1 if engine == "tc" else 0
     stream = torch.cuda.current_stream().cuda_stream
 
     def dom():
-        rc = lib.hf_contract(eng, 512, 784, BATCH, 1, A, B, c.data_ptr(), 784, None, 0, stream)
+        rc = lib.hf_contract(eng, BATCH, 512, 784, 1, A, B, c.data_ptr(), 512, None, 0, stream)
         assert rc == 0, lib.hf_last_error_string()
     t_dom = timed(dom)
-    f_dom = 2.0 * 512 * 784 * BATCH
+    f_dom = 2.0 * BATCH * 512 * 784
     roof = dict(bound="tensor", achieved=f_dom / (t_dom * 1e-3) / 1e12, peak=pk["tf"], unit="TFLOP/s",
-                frac=f_dom / (t_dom * 1e-3) / 1e12 / pk["tf"], traffic=None, peak_source=pk["src"],
-                kernel=f"contraction 512x784x4096 (layer-1 weight gradient), engine={engine}",
-                us_per_launch=1e3 * t_dom)
+                frac=f_dom / (t_dom * 1e-3) / 1e12 / pk["tf"],
+                traffic=17.9e6 if engine == "tc" else None,  # dram read+write per launch, ncu --set full (profiles/)
+                peak_source=pk["src"],
+                kernel=f"contraction 4096x512x784 (layer-1 R-op forward), engine={engine}",
+                us_per_launch=1e3 * t_dom,
+                note="3xTF32: three tensor-core MMAs per product, so the algorithmic ceiling is 1/6 of the bf16 peak")
     # fused CG vector update at the Martens-autoencoder size (P = 2,837,314: larger than cfg2 so that the pass is
     # bandwidth- rather than latency-bound) and at this workload's own P
     upd = {}
