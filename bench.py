@@ -78,7 +78,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -225,7 +225,13 @@ def run_native(args):
             e1.record()
             barrier()
             times.append(e0.elapsed_time(e1))
-    launches = lib.hf_debug_launch_count() - n0
+        launches = lib.hf_debug_launch_count() - n0
+        # nvidia-smi reports every ~100 ms and a 10-step timed region lasts ~0.1 s: keep the identical load running
+        # (untimed, same collectives on every rank) until the sampler has seen it
+        for _ in range(12):
+            for _ in range(4):
+                solve(prob, g, M)
+            torch.cuda.synchronize()
     assert why == "Number of iterations" and len(xs) == K_CG + 1, f"fixed-K solve stopped early: {why}, {len(xs) - 1} iterations"
     total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
     if world > 1:

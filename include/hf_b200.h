@@ -189,6 +189,15 @@ int hf_ggn_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* 
 int hf_hessian_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* d_out, int32_t accumulate,
                       const int32_t* d_skip, void* stream);
 
+/* The same products in two phases, for data-parallel callers that overlap communication with the sweep:
+ * phase 0 = tangent forward pass, loss Hessian and the transposed sweep except the parameter gradient of the first
+ * trainable layer; phase 1 = that gradient (the largest slice, formed last).  After phase 0 every entry of d_out
+ * outside the first layer's span is final.  kind: 0 = GGN, 1 = Hessian.                          */
+int hf_matvec_phase(hf_lin_t* lin, int32_t kind, const float* d_theta, const float* d_v, float* d_out, int32_t accumulate,
+                    const int32_t* d_skip, void* stream, int32_t phase);
+/* flat range [offset, offset+count) of the first trainable layer's parameters (count = 0 if not contiguous) */
+int hf_net_first_layer_span(const hf_net_t* net, int64_t* offset, int64_t* count);
+
 /* d_out (+)= sum_n g_n^2 ("sum") or (1/n_total) sum_n g_n^2 ("mean") on this chunk
  * (preconditioners.py:11-60 incl. the rescaling at :56-58).                                  */
 int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t accumulate, void* stream);

@@ -7,6 +7,7 @@
 //   hf_fisher_diag                    <- diag_EF_backpack, preconditioners.py:11-60
 // Activations are computed once per linearisation and stay resident in HBM for the whole solve (the
 // reference re-runs the forward pass for every chunk on every CG iteration, optimizer.py:805-814).
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -60,6 +61,8 @@ struct hf_lin {
   std::vector<float*> cot;    // cot[l]: cotangent dloss/dz_l (or its R-derivative) of the sweep in flight
   std::vector<float*> colbuf; // colbuf[l]: column-sum partials of cot[l] (bias gradient): [row blocks][out_l]
   size_t col_rows;            // row blocks each colbuf[l] can hold
+  const float* pending_cur;   // phased sweep: cotangent of the first trainable layer, left by phase 0 for phase 1
+  int pending_cols;
   cudaStream_t side;          // weight/bias gradients of layer l run here, concurrently with the data product that
   std::vector<cudaEvent_t> ev;  // continues the sweep on the caller's stream (ev[l]: cot[l] is ready)
   cudaEvent_t join;
@@ -426,8 +429,11 @@ enum BackMode { BACK_GRADIENT, BACK_GGN, BACK_FISHER, BACK_HESSIAN };
 //   GGN:      out (+)= J^T top
 //   FISHER:   out (+)= scale * sum_n (per-sample gradient)^2
 //   HESSIAN:  top = R{delta_L}; adds the delta_l^T R{a_{l-1}} and delta_l V_l terms and the act'' term
+// phase -1: the whole sweep.  phase 0: everything except the parameter gradient of the first trainable layer (whose
+// cotangent is left in lin->pending_cur).  phase 1: only that gradient.  The split lets a data-parallel caller start
+// the all-reduce of the upper layers' slices while the (largest, last) first-layer gradient is still being formed.
 static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const float* top, float* out, int accumulate,
-                          BackMode mode, const int32_t* skip, cudaStream_t stream) {
+                          BackMode mode, const int32_t* skip, cudaStream_t stream, int phase = -1) {
   const hf_net* net = lin->net;
   const int nl = (int)net->L.size();
   const bool keep = mode == BACK_GRADIENT && (lin->flags & HF_LIN_HESSIAN);
@@ -437,12 +443,18 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
   // The sweep is a chain of data products (cot[l] -> cot[l-1]) on the caller's stream; the parameter gradients of
   // layer l only need cot[l], so they run on the side stream while the chain moves on.  Every cotangent has its
   // own buffer, so there is no write-after-read hazard between the two streams.
-  const bool fork = lin->side != nullptr;
+  const bool fork = lin->side != nullptr && phase != 1;
   cudaStream_t gstream = fork ? lin->side : stream;
   const float* cur = top;
   int cur_col_tiles = 0;  // > 0: the kernel that produced `cur` also left its column sums in colbuf[l]
+  int l_start = nl - 1;
+  if (phase == 1) l_start = net->first_trainable, cur = lin->pending_cur, cur_col_tiles = lin->pending_cols;
   if (fork) HF_CUDA(cudaEventRecord(lin->ev[nl - 1], stream));
-  for (int l = nl - 1; l >= net->first_trainable; --l) {
+  for (int l = l_start; l >= net->first_trainable; --l) {
+    if (phase == 0 && l == net->first_trainable) {
+      lin->pending_cur = cur, lin->pending_cols = cur_col_tiles;
+      break;
+    }
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
     const int ld_in = l == 0 ? L.in : pad4(L.in), ld_out = pad4(L.out);
@@ -657,7 +669,7 @@ int hf_lin_create(const hf_net_t* net, int64_t batch, int32_t flags, void* d_wor
   lin->net = net, lin->N = batch, lin->flags = flags, lin->x = nullptr, lin->n_total = batch;
   lin->have_forward = lin->have_gradient = false;
   carve(net, batch, flags, static_cast<char*>(d_workspace), lin);
-  lin->side = nullptr, lin->join = nullptr;
+  lin->side = nullptr, lin->join = nullptr, lin->pending_cur = nullptr, lin->pending_cols = 0;
   if (!(flags & HF_LIN_LOSS_ONLY) && !getenv("HF_SINGLE_STREAM")) {
     // side stream + events for the forked gradient work; failure to create them only disables the overlap
     const int nl = (int)net->L.size();
@@ -752,6 +764,38 @@ int hf_ggn_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* 
   rc = apply_loss_hessian(lin, lin->buf[top], d_skip, stream);
   if (rc) return rc;
   return backward_sweep(lin, d_theta, d_v, lin->buf[top], d_out, accumulate, BACK_GGN, d_skip, stream);
+}
+
+int hf_matvec_phase(hf_lin_t* lin, int32_t kind, const float* d_theta, const float* d_v, float* d_out, int32_t accumulate,
+                    const int32_t* d_skip, void* stream_, int32_t phase) {
+  int rc = check_ready(lin, "hf_matvec_phase", kind == 1);
+  if (rc) return rc;
+  HF_REQUIRE((kind == 0 || kind == 1) && (phase == 0 || phase == 1), HF_ERR_INVALID, "hf_matvec_phase: bad kind/phase");
+  HF_REQUIRE(kind == 0 || (lin->flags & HF_LIN_HESSIAN), HF_ERR_INVALID, "hf_matvec_phase: linearisation lacks HF_LIN_HESSIAN");
+  HF_REQUIRE(d_v && d_out, HF_ERR_INVALID, "hf_matvec_phase: null vector");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const BackMode mode = kind == 1 ? BACK_HESSIAN : BACK_GGN;
+  if (phase == 0) {
+    int top = 0;
+    rc = rop_forward(lin, d_theta, d_v, kind == 1, d_skip, stream, &top);
+    if (rc) return rc;
+    rc = apply_loss_hessian(lin, lin->buf[top], d_skip, stream);
+    if (rc) return rc;
+    return backward_sweep(lin, d_theta, d_v, lin->buf[top], d_out, accumulate, mode, d_skip, stream, 0);
+  }
+  HF_REQUIRE(lin->pending_cur, HF_ERR_INVALID, "hf_matvec_phase: phase 1 without phase 0");
+  return backward_sweep(lin, d_theta, d_v, nullptr, d_out, accumulate, mode, d_skip, stream, 1);
+}
+
+int hf_net_first_layer_span(const hf_net_t* net, int64_t* offset, int64_t* count) {
+  HF_REQUIRE(net && offset && count, HF_ERR_INVALID, "hf_net_first_layer_span: null argument");
+  const Layer& L = net->L[net->first_trainable];
+  int64_t lo = INT64_MAX, hi = 0;
+  if (L.w_off >= 0) lo = std::min(lo, L.w_off), hi = std::max(hi, L.w_off + (int64_t)L.in * L.out);
+  if (L.has_bias && L.b_off >= 0) lo = std::min(lo, L.b_off), hi = std::max(hi, L.b_off + (int64_t)L.out);
+  int64_t sum = (L.w_off >= 0 ? (int64_t)L.in * L.out : 0) + ((L.has_bias && L.b_off >= 0) ? L.out : 0);
+  *offset = lo, *count = (hi - lo == sum) ? sum : 0;  // 0: the layer's slices are not adjacent in the flat vector
+  return HF_OK;
 }
 
 int hf_hessian_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* d_out, int32_t accumulate,

@@ -73,6 +73,12 @@ class NativeNet:
     def signature(self):
         return (tuple(l.signature() for l in self.layers), self.loss, self.reduction, self.n_params, self.engine)
 
+    def first_layer_span(self):
+        """(offset, count) of the first trainable layer's slice of the flat vector (count 0 if not contiguous)."""
+        off, cnt = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.hf_net_first_layer_span(self.handle, C.byref(off), C.byref(cnt)))
+        return off.value, cnt.value
+
     def linearize(self, x, targets, hessian=False, loss_only=False):
         return Linearization(self, x, targets, hessian=hessian, loss_only=loss_only)
 
@@ -130,6 +136,11 @@ class Linearization:
     def hessian(self, theta, v, out, accumulate=False, skip_ptr=None):
         _lib.check(self.lib.hf_hessian_matvec(self.handle, _lib.ptr(theta), v.data_ptr(), out.data_ptr(),
                                               int(accumulate), skip_ptr, _lib.stream()))
+
+    def matvec_phase(self, kind, theta, v, out, phase, accumulate=False, skip_ptr=None):
+        """Two-phase form of :meth:`ggn` / :meth:`hessian` (kind "ggn" | "hessian"); see ``hf_matvec_phase``."""
+        _lib.check(self.lib.hf_matvec_phase(self.handle, int(kind == "hessian"), _lib.ptr(theta), v.data_ptr(),
+                                            out.data_ptr(), int(accumulate), skip_ptr, _lib.stream(), int(phase)))
 
     def fisher(self, theta, out, accumulate=False):
         _lib.check(self.lib.hf_fisher_diag(self.handle, _lib.ptr(theta), out.data_ptr(), int(accumulate), _lib.stream()))

@@ -34,6 +34,10 @@ class NativeProblem:
             else [net.linearize(x, t, loss_only=True) for x, t in loss_data]
         self.n_mvp, self.n_grad, self.n_loss = (self._count(l) for l in (self.mvp_lins, self.grad_lins, self.loss_lins))
         self._cand = torch.empty_like(theta)
+        self.overlap_allreduce = False
+        off, cnt = net.first_layer_span()
+        # the overlap split needs the first layer's slice to be a 16-byte aligned prefix of the flat vector
+        self._split_at = cnt if (off == 0 and 0 < cnt < theta.numel() and cnt % 4 == 0) else 0
         self._linearized = False
 
     def _count(self, lins):
@@ -77,7 +81,24 @@ class NativeProblem:
 
     # ---- once per CG iteration ---------------------------------------------------------------------
     def matvec(self, v, out, skip_ptr=None):
-        """``out = B v`` (no damping), enqueued without host synchronisation."""
+        """``out = B v`` (no damping), enqueued without host synchronisation.
+
+        Data-parallel: one all-reduce(sum) of the flat vector after the local chunk sum.  With
+        ``overlap_allreduce`` (off by default) and one chunk per rank the sweep runs in two phases and the
+        all-reduce of the upper layers' slices (final after phase 0) overlaps with the first layer's weight
+        gradient.  Measured on 4 B200 with NCCL at cfg2's P = 669 706: two collectives cost more fixed latency than
+        the overlap hides (16.6 vs 14.6 ms per 50-iteration solve), hence the default."""
+        if self.overlap_allreduce and self.group is not None and len(self.mvp_lins) == 1 and self._split_at > 0:
+            import torch.distributed as dist
+
+            lin, n0 = self.mvp_lins[0], self._split_at
+            lin.matvec_phase(self.curvature_opt, self.theta, v, out, 0, skip_ptr=skip_ptr)
+            upper = dist.all_reduce(out[n0:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            lin.matvec_phase(self.curvature_opt, self.theta, v, out, 1, skip_ptr=skip_ptr)
+            first = dist.all_reduce(out[:n0], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            upper.wait()
+            first.wait()
+            return
         for i, lin in enumerate(self.mvp_lins):
             if self.curvature_opt == "hessian":
                 lin.hessian(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)

@@ -137,3 +137,31 @@ def test_linearity_and_symmetry_at_full_width(engine):
     a, b = torch.dot(v.double(), Bw.double()).item(), torch.dot(w.double(), Bv.double()).item()
     assert abs(a - b) <= 1e-4 * max(abs(a), abs(b), 1e-12)
     assert torch.dot(v.double(), Bv.double()).item() >= 0.0
+
+
+@pytest.mark.parametrize("curv", ["ggn", "hessian"])
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_two_phase_product_equals_single_call(curv, engine):
+    """hf_matvec_phase (the data-parallel overlap seam) must reproduce hf_ggn_matvec / hf_hessian_matvec bit for bit."""
+    spec = dict(widths=[784, 512, 512, 10], act="relu", bias=[True] * 3, frozen=[], loss="ce")
+    torch.manual_seed(0)
+    model = build_model(spec).to(DEV)
+    loss_fn = build_loss(spec, "mean")
+    x, t = (a.to(DEV) for a in make_data(spec, 1024, 0))
+    params = list(model.parameters())
+    prog = lower_module(model, loss_fn, params)
+    theta = torch.cat([p.detach().reshape(-1) for p in params])
+    net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine)
+    prob = NativeProblem(net, theta, curv, [(x, t)])
+    prob.linearize(), prob.gradient()
+    v = torch.randn_like(theta)
+    want = prob.mvp(v)
+    off, cnt = net.first_layer_span()
+    assert (off, cnt) == (0, 784 * 512 + 512)
+    got = torch.full_like(theta, float("nan"))
+    lin = prob.mvp_lins[0]
+    lin.matvec_phase(curv, theta, v, got, 0)
+    torch.cuda.synchronize()
+    assert torch.isnan(got[:cnt]).all() and torch.equal(got[cnt:], want[cnt:])
+    lin.matvec_phase(curv, theta, v, got, 1)
+    assert torch.equal(got, want)
