@@ -89,12 +89,17 @@ class HessianFree(torch.optim.Optimizer):
         if len(self.param_groups) != 1:
             raise ValueError("`HessianFree` does not support per-parameter options.")
         self.verbose = verbose
-        self._group = self.param_groups[0]
         self._params = self._group["params"]
         self._params_list = [p for p in self._params if p.requires_grad]  # the subspace everything lives in
         self.device = self._params_list[0].device
         self._theta = None
         self._nets = {}
+
+    @property
+    def _group(self):
+        """The one parameter group.  Looked up on every use: ``load_state_dict`` replaces the group dicts, and an
+        alias taken in ``__init__`` (as in the reference, ``optimizer.py:118``) would keep reading the old damping."""
+        return self.param_groups[0]
 
     # ------------------------------------------------------------------------------------------------
     # flat parameter buffer
