@@ -22,7 +22,13 @@
 
 namespace hf {
 
-constexpr int BM = 128, BN = 128, BKT = 32;  // tile; BKT floats = 128 B = one swizzle row
+// Tile 128x128, k-block of BKT floats.  BKT = 32: 128-byte swizzle rows, 193 KB of shared memory, one CTA per SM.
+// BKT = 16 (64-byte rows, 97 KB, two CTAs per SM) is supported by every piece below and was measured: the co-resident
+// CTAs overlap each other's prologue/epilogue, but the main loop pays one mbarrier round trip per 16 instead of 32
+// columns (1.15 vs 0.73 us per 32 columns) and the product got 10 % slower, so 32 it is.
+constexpr int BM = 128, BN = 128, BKT = 32;
+constexpr int kCtasPerSm = BKT == 32 ? 1 : 2;
+constexpr uint32_t kKMajorLayout = BKT == 32 ? 2u : 4u;  // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BKT * 4;                  // 16 KB per operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;               // rawA | rawB | loA | loB
@@ -117,12 +123,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   return d;
 }
 // operand tile of 128 (M or N) x 32 (K) floats at `base`, k-step ks (8 floats):
-//   K-major : SWIZZLE_128B (type 2): rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); step = +32 B in the row
+//   K-major : rows of BKT*4 bytes (SWIZZLE_128B, type 2, for BKT = 32; SWIZZLE_64B, type 4, for BKT = 16), 8-row
+//             swizzle atoms 8*BKT*4 bytes apart (SBO); step = +32 B in the row
 //   MN-major: 32-bit operands only exist in SWIZZLE_128B_BASE32B (type 1; cute Layout_MN_SW128_32B_Atom, TMA
 //             SWIZZLE_128B_ATOM_32B): atoms of [4 k-rows x 128 B] 512 B apart along K (SBO); 4 column blocks of
 //             [32 k-rows x 128 B] 4096 B apart along MN (LBO); one k-step = 8 k-rows = +1024 B
 __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int mn_major, int ks) {
-  return mn_major ? smem_desc(base + ks * 1024, BKT * 128, 512, 1) : smem_desc(base + ks * 32, 16, 1024, 2);
+  return mn_major ? smem_desc(base + ks * 1024, BKT * 128, 512, 1) : smem_desc(base + ks * 32, 16, 8 * BKT * 4, kKMajorLayout);
 }
 
 // ---- fused epilogue, one specialisation per (epilogue kind, activation): the row loop is straight-line vector code
@@ -283,7 +290,7 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const float
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, kCtasPerSm)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ TcArgs p) {
   const GemmArgs& g = p.g;
@@ -497,7 +504,8 @@ static int make_map(CUtensorMap* map, const Operand& op, int MN, int K) {
   }
   CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(op.ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                    : (BKT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HF_REQUIRE(r == CUDA_SUCCESS, HF_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
