@@ -61,6 +61,10 @@ struct hf_lin {
   std::vector<float*> cot;    // cot[l]: cotangent dloss/dz_l (or its R-derivative) of the sweep in flight
   std::vector<float*> colbuf; // colbuf[l]: column-sum partials of cot[l] (bias gradient): [row blocks][out_l]
   size_t col_rows;            // row blocks each colbuf[l] can hold
+  // Layers whose fan-in is not a multiple of 4 floats cannot be addressed by TMA in place (16-byte row pitch): the
+  // tensor engine reads 16-byte-pitched copies instead.  wpad[l] is refreshed by hf_lin_forward (weights are fixed
+  // for the life of a linearisation), vpad[l] at the start of every product.
+  std::vector<float*> wpad, vpad;
   const float* pending_cur;   // phased sweep: cotangent of the first trainable layer, left by phase 0 for phase 1
   int pending_cols;
   cudaStream_t side;          // weight/bias gradients of layer l run here, concurrently with the data product that
@@ -223,6 +227,40 @@ static inline const float* bias_ptr(const Layer& l, const float* theta) {
   return l.b_off >= 0 ? theta + l.b_off : l.b_frozen;
 }
 
+// dst[r][0..ld) = src[r][0..cols) padded with zeros
+__global__ void pitch_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int ld,
+                                  const int32_t* __restrict__ skip) {
+  if (skip && *skip) return;
+  const int64_t total = (int64_t)rows * ld;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld), c = (int)(i % ld);
+    dst[i] = c < cols ? src[(int64_t)r * cols + c] : 0.f;
+  }
+}
+
+static int pitch_rows(const float* src, float* dst, int rows, int cols, const int32_t* skip, cudaStream_t stream) {
+  const int ld = pad4(cols);
+  int64_t blocks = ((int64_t)rows * ld + 255) / 256;
+  if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+  pitch_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, rows, cols, ld, skip);
+  HF_LAUNCH_CHECK();
+  return HF_OK;
+}
+
+// weight / direction operand of layer l as the kernels should read it: in place, or the 16-byte-pitched copy
+static inline Operand w_operand(const hf_lin* lin, int l, const float* theta, bool k_contig) {
+  const Layer& L = lin->net->L[l];
+  const float* p = lin->wpad[l] ? lin->wpad[l] : weight_ptr(L, theta);
+  const int ld = lin->wpad[l] ? pad4(L.in) : L.in;
+  return k_contig ? Operand{p, ld, 1} : Operand{p, 1, ld};
+}
+static inline Operand v_operand(const hf_lin* lin, int l, const float* v, bool k_contig) {
+  const Layer& L = lin->net->L[l];
+  const float* p = lin->vpad[l] ? lin->vpad[l] : v + L.w_off;
+  const int ld = lin->vpad[l] ? pad4(L.in) : L.in;
+  return k_contig ? Operand{p, ld, 1} : Operand{p, 1, ld};
+}
+
 struct SplitPlan {
   int splits;
   int k_per_split;
@@ -346,6 +384,11 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
   const int nl = (int)net->L.size();
   const float* cur = nullptr;
   int which = 0;
+  for (int l = net->first_trainable; l < nl; ++l)
+    if (lin->vpad[l]) {
+      int rc = pitch_rows(v + net->L[l].w_off, lin->vpad[l], net->L[l].out, net->L[l].in, skip, stream);
+      if (rc) return rc;
+    }
   for (int l = net->first_trainable; l < nl; ++l) {
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
@@ -354,11 +397,11 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
     g.M = (int)lin->N, g.N = L.out, g.K = L.in;
     int np = 0;
     if (L.w_off >= 0) {
-      g.A[np] = op_kc(a_in, ld_in), g.B[np] = op_kc(v + L.w_off, L.in);
+      g.A[np] = op_kc(a_in, ld_in), g.B[np] = v_operand(lin, l, v, true);
       ++np;
     }
     if (cur) {
-      g.A[np] = op_kc(cur, ld_in), g.B[np] = op_kc(weight_ptr(L, theta), L.in);
+      g.A[np] = op_kc(cur, ld_in), g.B[np] = w_operand(lin, l, theta, true);
       ++np;
     }
     float* dst = (hessian && l < nl - 1) ? lin->ra[l] : lin->buf[which];
@@ -478,9 +521,9 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       GemmArgs g = blank_gemm();
       g.M = (int)lin->N, g.N = L.in, g.K = L.out;
       int np = 0;
-      g.A[np] = op_kc(cur, ld_out), g.B[np] = op_mnc(weight_ptr(L, theta), L.in), ++np;
+      g.A[np] = op_kc(cur, ld_out), g.B[np] = w_operand(lin, l, theta, false), ++np;
       if (mode == BACK_HESSIAN && L.w_off >= 0) {
-        g.A[np] = op_kc(lin->delta[l], ld_out), g.B[np] = op_mnc(v + L.w_off, L.in), ++np;
+        g.A[np] = op_kc(lin->delta[l], ld_out), g.B[np] = v_operand(lin, l, v, false), ++np;
       }
       g.n_pairs = np;
       float* dst = keep ? lin->delta[l - 1] : lin->cot[l - 1];
@@ -621,6 +664,18 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   const int fwd_max = (!loss_only && net->classes <= 32) ? 16 : 0;
   float* pfwd = fwd_max ? (float*)take(sizeof(float) * fwd_max * N * pad4(net->classes)) : nullptr;
   if (lin) lin->partial_fwd = pfwd, lin->fwd_splits_max = fwd_max, lin->fwd_splits = 0, lin->fwd_bias = nullptr;
+  if (lin) lin->wpad.assign(nl, nullptr), lin->vpad.assign(nl, nullptr);
+  if (!loss_only && net->engine == 1)
+    for (int l = net->first_trainable; l < nl; ++l) {
+      const Layer& L = net->L[l];
+      // in place needs a 16-byte row pitch AND a 16-byte aligned slice start (the flat offset of a layer depends on
+      // the sizes of all layers before it: after a 30- or 250-wide layer every later slice is misaligned)
+      const bool aligned = L.w_off >= 0 ? L.w_off % 4 == 0 : (reinterpret_cast<uintptr_t>(L.w_frozen) & 15u) == 0;
+      if (L.in % 4 == 0 && aligned) continue;
+      float* wp = (float*)take(sizeof(float) * L.out * pad4(L.in));
+      float* vp = L.w_off >= 0 ? (float*)take(sizeof(float) * L.out * pad4(L.in)) : nullptr;
+      if (lin) lin->wpad[l] = wp, lin->vpad[l] = vp;
+    }
   const size_t col_rows = (size_t)std::max<int64_t>(colsum_plan(N), (N + 127) / 128);
   if (lin) lin->cot.assign(nl, nullptr), lin->colbuf.assign(nl, nullptr), lin->col_rows = col_rows;
   if (!loss_only)
@@ -709,6 +764,10 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     g.A[0] = op_kc(l == 0 ? d_x : lin->a[l - 1], l == 0 ? L.in : pad4(L.in));
     g.B[0] = op_kc(weight_ptr(L, d_theta), L.in);
     g.C = lin->a[l], g.ldc = pad4(L.out);
+    if (lin->wpad[l]) {  // weights are fixed from here on: refresh the 16-byte-pitched copy the tensor engine reads
+      int rcp = pitch_rows(weight_ptr(L, d_theta), lin->wpad[l], L.out, L.in, nullptr, stream);
+      if (rcp) return rcp;
+    }
     g.epi = EPI_BIAS_ACT, g.act = L.act, g.bias = bias_ptr(L, d_theta);
     // The linearisation point fixes the ReLU masks for the whole solve, so it is evaluated in plain FP32: the
     // ~5e-6 error of the 3xTF32 tiles would flip a few dozen of the 4M masks of the MLP config (each flip moves a
