@@ -71,6 +71,10 @@ __device__ __forceinline__ void store_vec(T* __restrict__ base, int64_t g, int64
   }
 }
 
+__device__ __forceinline__ void l2_prefetch(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // rounding-faithful a + s*b (two roundings, like the reference's out-of-place `x + alpha * p`)
 __device__ __forceinline__ float mul_add(float s, float b, float a) { return __fadd_rn(a, __fmul_rn(s, b)); }
 __device__ __forceinline__ double mul_add(double s, double b, double a) { return __dadd_rn(a, __dmul_rn(s, b)); }
@@ -160,6 +164,12 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
     for (int j = threadIdx.x; j < nloc; j += kThreads) {
       const V p4 = load_vec(a.p, g0 + j, a.P);
       V q4 = load_vec(a.Bp, g0 + j, a.P);
+      // Pull the operands of phase 2 into L2 now: HBM then streams all six inputs back to back while the grid-wide
+      // reduction below is in flight, instead of idling until alpha is known.
+      l2_prefetch(a.x + (g0 + j) * N);
+      l2_prefetch(a.r + (g0 + j) * N);
+      l2_prefetch(a.b + (g0 + j) * N);
+      if (a.minv) l2_prefetch(a.minv + (g0 + j) * N);
 #pragma unroll
       for (int e = 0; e < N; ++e) {
         q4.v[e] = mul_add(lam, p4.v[e], q4.v[e]);

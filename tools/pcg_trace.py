@@ -18,6 +18,8 @@ for P in (669706, 2837314):
     e1.record(); torch.cuda.synchronize()
     print(f"P={P}: back-to-back {e0.elapsed_time(e1)*1e3/50:.2f} us per launch")
     _lib.check(lib.hf_debug_pcg_trace(tr.data_ptr()))
+    if len(sys.argv) > 1 and sys.argv[1] == "cold":
+        torch.empty(256 << 20, dtype=torch.uint8, device=dev).fill_(1); torch.cuda.synchronize()
     s.iterate(PCG_FUSED, Bp=Bp, minv=minv, lam=1e-3); torch.cuda.synchronize()
     _lib.check(lib.hf_debug_pcg_trace(None))
     n = lib.hf_device_sm_count()
