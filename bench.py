@@ -346,7 +346,8 @@ def kernel_rooflines(lib, prob, theta, dev, pk, engine):
                 peak_source=pk["src"],
                 kernel=f"contraction 4096x512x784 (layer-1 R-op forward), engine={engine}",
                 us_per_launch=1e3 * t_dom,
-                note="3xTF32: three tensor-core MMAs per product, so the algorithmic ceiling is 1/6 of the bf16 peak")
+                note="split precision (TF32 main term + two BF16 correction terms = 4 bf16-MMA equivalents per product), "
+                     "so the algorithmic ceiling is 1/4 of the bf16 peak")
     # fused CG vector update at the Martens-autoencoder size (P = 2,837,314: larger than cfg2 so that the pass is
     # bandwidth- rather than latency-bound) and at this workload's own P
     upd = {}

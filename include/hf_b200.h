@@ -156,7 +156,7 @@ typedef struct {
 int hf_net_create(const hf_layer_desc* layers, int32_t n_layers, int32_t loss, int32_t reduction, int64_t n_params,
                   hf_net_t** out);
 void hf_net_destroy(hf_net_t* net);
-/* contraction engine: 0 = FP32 SIMT tiles for every layer, 1 = tcgen05 3xTF32 tiles wherever the layer
+/* contraction engine: 0 = FP32 SIMT tiles for every layer, 1 = tcgen05 split-precision tiles wherever the layer
  * shape meets the TMA alignment rules (feature widths multiples of 4 floats), SIMT otherwise.   */
 int hf_net_set_engine(hf_net_t* net, int32_t engine);
 
@@ -208,7 +208,7 @@ const float* hf_lin_logits(const hf_lin_t* lin);
 /* ------------------------------------------------------------------------------------------
  * Stand-alone contraction used by the kernels above, exported for unit tests and profiling:
  * C[M,N] = sum_s A_s[M,K] * B_s[N,K]^T  (n_pairs in {1,2}), element strides given per operand.
- * engine: 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32 tiles (requires the alignment it reports).
+ * engine: 0 = FP32 SIMT tiles, 1 = tcgen05 split-precision tiles (requires the alignment it reports).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const float* d_ptr;

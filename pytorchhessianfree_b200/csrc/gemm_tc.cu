@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA contraction engine in 3xTF32 split precision (sm_100a).
+// tcgen05 / TMEM / TMA contraction engine in split precision: TF32 main term + two BF16 correction terms (sm_100a).
 //
 //   C[M,N] = epilogue( sum_{s < n_pairs} A_s[M,K] * B_s[N,K]^T )        (same contract as gemm_simt.cuh)
 //
@@ -9,11 +9,17 @@
 //            transposed copy of any activation or weight is ever made.  Out-of-bounds rows/columns are zero-filled
 //            by the TMA unit, which is what makes ragged M, N, K (784 = 24.5 x 32) legal.
 //   warps0-3 splitters, then epilogue.  kind::tf32 keeps the top 19 bits of each FP32 word (truncation), so the raw
-//            tile already is the "hi" operand; the splitters write lo = x - trunc_tf32(x) (exact in FP32) into a
-//            second buffer with the identical swizzled layout (the op is element-wise, so the swizzle is irrelevant).
-//   warp 5   MMA issuer (one elected lane): per 8-wide k-step three tcgen05.mma.kind::tf32 into the same TMEM
-//            accumulator: A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.  The dropped lo*lo term is ~2^-22 relative, so
-//            products are FP32-faithful (rtol 1e-4 needs ~2^-13).  tcgen05.commit releases the smem stage.
+//            tile already is the "hi" operand x_t.  The splitters turn each raw tile into two BF16 tiles of the same
+//            major-ness in the canonical 16-bit UMMA layouts: lo16 = bf16(x - x_t) (the remainder is exact in FP32)
+//            and hi16 = bf16(x).
+//   warp 5   MMA issuer (one elected lane): per 32-wide k-block four tcgen05.mma.kind::tf32 (A_t*B_t, K = 8 each) and
+//            four tcgen05.mma.kind::f16 (A_lo16*B_hi16 + A_hi16*B_lo16, K = 16 each) into the same TMEM accumulator.
+//            Error budget per product: the dropped lo*lo term is 2^-22; the BF16 rounding of a correction operand is
+//            2^-9 of a term that is itself 2^-11 of the product, i.e. ~2^-19 with random sign -- FP32-faithful at the
+//            rtol 1e-4 the path needs (~2^-13).  All-TF32 corrections (3xTF32) measured the same accuracy in the
+//            parity suite and 1.2x the main-loop time: the loop is bound by shared-memory bytes (TMA writes, splitter
+//            read/write, MMA operand reads), and the BF16 tiles halve the correction terms' operand bytes.
+//            tcgen05.commit releases the smem stage.
 //   epilogue tcgen05.ld 32x32b -> registers -> the same fused epilogues as the SIMT engine (bias, act', act'', raw
 //            copy, split-K partials) -> global.
 #include <cuda.h>
@@ -89,6 +95,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // round to the nearest TF32 value (the MMA unit would otherwise truncate the low word: a bias of ~2^-22 per operand)
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
@@ -130,6 +144,52 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 //             [32 k-rows x 128 B] 4096 B apart along MN (LBO); one k-step = 8 k-rows = +1024 B
 __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int mn_major, int ks) {
   return mn_major ? smem_desc(base + ks * 1024, BKT * 128, 512, 1) : smem_desc(base + ks * 32, 16, 8 * BKT * 4, kKMajorLayout);
+}
+
+// BF16 correction tile of 128 (M or N) x 32 (K) bf16 at `base`, k-step ks (16 bf16):
+//   K-major : 64-byte rows, SWIZZLE_64B (type 4), 8-row atoms 512 B apart (SBO); step = +32 B in the row
+//   MN-major: two column blocks of [32 k-rows x 128 B = 64 bf16] 4096 B apart along MN (LBO), SWIZZLE_128B (type 2),
+//             atoms of 8 k-rows 1024 B apart along K (SBO); one k-step = 16 k-rows = +2048 B
+__device__ __forceinline__ uint64_t corr_desc(uint32_t base, int mn_major, int ks) {
+  return mn_major ? smem_desc(base + ks * 2048, 4096, 1024, 2) : smem_desc(base + ks * 32, 16, 512, 4);
+}
+
+// Splitter: one FP32 operand tile (in its UMMA/TMA swizzled layout) -> two BF16 tiles of the same major-ness:
+// hi16 = bf16(x) and lo16 = bf16(x - trunc_tf32(x)).  The FP32 tile is element (row, k-quad) addressed by undoing the
+// TMA swizzle; the BF16 tiles are written in the canonical UMMA layout for 16-bit operands.
+template <bool MN>
+__device__ __forceinline__ void split_tile(uint32_t src, uint32_t lo16, uint32_t hi16) {  // shared-space addresses
+  // element i = tid + 128 t (t = 0..7) of the FP32 tile is the float4 at src + 16 i; all swizzle arithmetic depends on
+  // tid only and is hoisted, the t-dependence is a compile-time constant
+  const int tid = threadIdx.x, r0 = tid >> 3, pc = tid & 7;
+  int off0;
+  if (!MN) {  // source [128 rows][8 x 16 B], chunk ^= row & 7 (SWIZZLE_128B); row = r0 + 16 t
+    const int j = pc ^ (r0 & 7);
+    off0 = r0 * 64 + ((((j >> 1) ^ (r0 >> 1)) & 3) << 4) + ((j & 1) << 3);
+  } else {    // source: 4 column blocks of [32 k-rows][4 x 32 B], 32-byte chunk ^= k-row & 3 (SWIZZLE_128B_ATOM_32B);
+              // column block = t >> 1, k-row = r0 + 16 (t & 1)
+    const int m0 = (((pc >> 1) ^ r0) & 3) * 8 + (pc & 1) * 4;
+    off0 = r0 * 128 + ((((m0 >> 3) ^ r0) & 7) << 4) + ((m0 & 4) << 1);
+  }
+  float4 v[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[t].x), "=f"(v[t].y), "=f"(v[t].z), "=f"(v[t].w) : "r"(src + 16 * tid + 2048 * t));
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float lx = v[t].x - __uint_as_float(__float_as_uint(v[t].x) & 0xffffe000u);
+    const float ly = v[t].y - __uint_as_float(__float_as_uint(v[t].y) & 0xffffe000u);
+    const float lz = v[t].z - __uint_as_float(__float_as_uint(v[t].z) & 0xffffe000u);
+    const float lw = v[t].w - __uint_as_float(__float_as_uint(v[t].w) & 0xffffe000u);
+    uint32_t h0, h1, l0, l1;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v[t].y), "f"(v[t].x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v[t].w), "f"(v[t].z));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l0) : "f"(ly), "f"(lx));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l1) : "f"(lw), "f"(lz));
+    const int off = MN ? (t >> 2) * 4096 + (t & 1) * 2048 + (off0 ^ (((t >> 1) & 1) << 6)) : off0 + 1024 * t;
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(lo16 + off), "r"(l0), "r"(l1) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(hi16 + off), "r"(h0), "r"(h1) : "memory");
+  }
 }
 
 // ---- fused epilogue, one specialisation per (epilogue kind, activation): the row loop is straight-line vector code
@@ -178,7 +238,7 @@ __device__ __forceinline__ void st4(float* p, int cnt, const float (&o)[4]) {
 
 // rows [m_base, m_base+32) x columns [n, n+4) of the tile; `stage` holds the warp's 32 accumulator rows
 template <int EPI, int ACT, bool VEC>
-__device__ __forceinline__ void epilogue_rows(const GemmArgs& g, const float* stage, int m_base, int n, int lane, int cnt,
+__device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t stage, int m_base, int n, int lane, int cnt,
                                               float (&cs)[4]) {
   constexpr int LDS_ROW = BN + 4;
   constexpr bool NEED_AUX = ACT != HF_ACT_NONE && EPI >= EPI_BIAS_DACT;
@@ -203,7 +263,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, const float* st
     for (int j = 0; j < RB; ++j) {
       const int r = min(r0 + j, rows - 1);  // clamp: tail slots re-read the last row and are not stored
       const int64_t m = m_base + r;
-      const float4 t = *reinterpret_cast<const float4*>(stage + r * LDS_ROW + lane * 4);
+      float4 t;  // explicit shared-space load (the pointer's address space is not visible to the compiler here)
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(stage + (r * LDS_ROW + lane * 4) * 4));
       x[j][0] = t.x, x[j][1] = t.y, x[j][2] = t.z, x[j][3] = t.w;
       if (NEED_AUX) ld4<VEC>(aux + m * ldaux, cnt, au[j]);
       if (EPI == EPI_DACT_H && hga) {
@@ -254,7 +315,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, const float* st
 }
 
 template <int EPI, int ACT>
-__device__ __forceinline__ void epilogue_vec(const GemmArgs& g, const float* stage, int m_base, int n, int lane,
+__device__ __forceinline__ void epilogue_vec(const GemmArgs& g, uint32_t stage, int m_base, int n, int lane,
                                              float (&cs)[4]) {
   const int cnt = min(4, g.N - n);
   if (cnt <= 0 || m_base >= g.M) return;
@@ -269,7 +330,7 @@ __device__ __forceinline__ void epilogue_vec(const GemmArgs& g, const float* sta
 }
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_act(const GemmArgs& g, const float* stage, int m_base, int n, int lane,
+__device__ __forceinline__ void epilogue_act(const GemmArgs& g, uint32_t stage, int m_base, int n, int lane,
                                              float (&cs)[4]) {
   switch (g.act) {
     case HF_ACT_RELU: epilogue_vec<EPI, HF_ACT_RELU>(g, stage, m_base, n, lane, cs); break;
@@ -279,7 +340,7 @@ __device__ __forceinline__ void epilogue_act(const GemmArgs& g, const float* sta
   }
 }
 
-__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const float* stage, int m_base, int n, int lane,
+__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, uint32_t stage, int m_base, int n, int lane,
                                                float (&cs)[4]) {
   switch (g.epi) {
     case EPI_STORE: epilogue_vec<EPI_STORE, HF_ACT_NONE>(g, stage, m_base, n, lane, cs); break;
@@ -370,14 +431,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait(&full_lo[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t rawA = smem_u32(tiles + s * STAGE_BYTES), rawB = rawA + TILE_BYTES;
-        const uint32_t loA = rawA + 2 * TILE_BYTES, loB = rawA + 3 * TILE_BYTES;
+        // corrections in BF16 (half the tensor time of a TF32 MMA): A_lo*B_hi + A_hi*B_lo with 8-bit operands is
+        // 2^-10 * 2^-8 = 2^-18 relative per product, random sign
+        const uint32_t idesc16 = (idesc & ~((7u << 7) | (7u << 10))) | (1u << 7) | (1u << 10);
+        const uint32_t loA = rawA + 2 * TILE_BYTES, hiA = loA + TILE_BYTES / 2, loB = hiA + TILE_BYTES / 2, hiB = loB + TILE_BYTES / 2;
 #pragma unroll
-        for (int ks = 0; ks < BKT / 8; ++ks) {
-          const uint64_t a_hi = operand_desc(rawA, p.a_mn[pr], ks), b_hi = operand_desc(rawB, p.b_mn[pr], ks);
-          const uint64_t a_lo = operand_desc(loA, p.a_mn[pr], ks), b_lo = operand_desc(loB, p.b_mn[pr], ks);
-          umma_tf32(tmem_base, a_lo, b_hi, idesc, (it | ks) != 0);
-          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        for (int ks = 0; ks < BKT / 8; ++ks)
+          umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], ks), operand_desc(rawB, p.b_mn[pr], ks), idesc, (it | ks) != 0);
+#pragma unroll
+        for (int ks = 0; ks < BKT / 16; ++ks) {
+          umma_bf16(tmem_base, corr_desc(loA, p.a_mn[pr], ks), corr_desc(hiB, p.b_mn[pr], ks), idesc16, 1);
+          umma_bf16(tmem_base, corr_desc(hiA, p.a_mn[pr], ks), corr_desc(loB, p.b_mn[pr], ks), idesc16, 1);
         }
         umma_commit(&empty[s]);
       }
@@ -385,22 +449,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else {
     // ---------------- splitters ----------------
+    int sp_pr = 0, sp_kb = 0;
     for (int it = 0; it < total; ++it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(&full_raw[s], ph);
       if (it == 0) tc_mark(2, threadIdx.x == 0);
-      const float4* src = reinterpret_cast<const float4*>(tiles + s * STAGE_BYTES);
-      float4* dst = reinterpret_cast<float4*>(tiles + s * STAGE_BYTES + 2 * TILE_BYTES);
-#pragma unroll 4
-      for (int i = threadIdx.x; i < 2 * TILE_BYTES / 16; i += 128) {
-        const float4 v = src[i];
-        float4 lo;
-        lo.x = tf32_round(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
-        lo.y = tf32_round(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
-        lo.z = tf32_round(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
-        lo.w = tf32_round(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
-        dst[i] = lo;
-      }
+      const uint32_t st = smem_u32(tiles + s * STAGE_BYTES);
+      if (p.a_mn[sp_pr]) split_tile<true>(st, st + 2 * TILE_BYTES, st + 2 * TILE_BYTES + TILE_BYTES / 2);
+      else split_tile<false>(st, st + 2 * TILE_BYTES, st + 2 * TILE_BYTES + TILE_BYTES / 2);
+      if (p.b_mn[sp_pr]) split_tile<true>(st + TILE_BYTES, st + 3 * TILE_BYTES, st + 3 * TILE_BYTES + TILE_BYTES / 2);
+      else split_tile<false>(st + TILE_BYTES, st + 3 * TILE_BYTES, st + 3 * TILE_BYTES + TILE_BYTES / 2);
+      if (++sp_kb == n_kb) sp_kb = 0, ++sp_pr;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA unit
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_lo[s]);
@@ -414,7 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     tc_mark(3, threadIdx.x == 0);
     constexpr int LDS_ROW = BN + 4;
-    float* stage = reinterpret_cast<float*>(tiles) + warp * 32 * LDS_ROW;
+    const uint32_t stage = smem_u32(tiles) + warp * 32 * LDS_ROW * 4;
 #pragma unroll 2
     for (int c = 0; c < BN; c += 16) {
       float v[16];
@@ -426,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
 #pragma unroll
       for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(stage + lane * LDS_ROW + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + (lane * LDS_ROW + c + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
     }
     __syncwarp();
     tc_mark(5, threadIdx.x == 0);

@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA contraction engine (3xTF32 split precision) -- interface.
+// tcgen05 / TMEM / TMA contraction engine (split precision: TF32 + BF16 corrections) -- interface.
 #pragma once
 #include "gemm_simt.cuh"
 

@@ -770,7 +770,7 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     }
     g.epi = EPI_BIAS_ACT, g.act = L.act, g.bias = bias_ptr(L, d_theta);
     // The linearisation point fixes the ReLU masks for the whole solve, so it is evaluated in plain FP32: the
-    // ~5e-6 error of the 3xTF32 tiles would flip a few dozen of the 4M masks of the MLP config (each flip moves a
+    // ~5e-6 error of the split-precision tensor tiles would flip a few dozen of the 4M masks of the MLP config (each flip moves a
     // gradient row by ~1/sqrt(N)).  Loss-only evaluations (line search, backtracking) have no masks to fix and
     // stay on the tensor-core tiles.
     int rc = (lin->flags & HF_LIN_LOSS_ONLY) ? run_gemm(net, g, stream) : launch_gemm_simt(g, stream);

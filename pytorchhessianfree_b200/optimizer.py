@@ -60,7 +60,7 @@ class HessianFree(torch.optim.Optimizer):
         """Arguments up to ``verbose`` are the reference's (``optimizer.py:23-77``).
 
         Keyword-only extensions: ``martens_conv_crit`` (use Martens' relative-progress stopping rule in CG),
-        ``engine`` ("auto" | "tc" | "simt": tensor-core 3xTF32 tiles where the layer shapes allow, or FP32
+        ``engine`` ("auto" | "tc" | "simt": split-precision (TF32 + BF16 corrections) tensor-core tiles where the layer shapes allow, or FP32
         SIMT tiles everywhere), ``process_group`` (data-parallel group over which ``acc_step`` chunks are
         sharded; None = single GPU).
         """

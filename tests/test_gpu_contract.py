@@ -35,8 +35,8 @@ def run_contract(engine, A_list, B_list, layouts):
     return C
 
 
-# engine 0: FP32 FMA tiles.  engine 1: 3xTF32 tensor-core tiles (hi = truncated word, lo = exact remainder, lo*lo
-# dropped): ~2^-19 relative, two orders inside the rtol 1e-4 the curvature products have to meet.
+# engine 0: FP32 FMA tiles.  engine 1: split-precision tensor-core tiles (TF32 hi = truncated word, BF16 corrections
+# from the exact remainder, lo*lo dropped): ~2^-19 relative, two orders inside the rtol 1e-4 the curvature products have to meet.
 TOL = {0: 2e-6, 1: 2e-5}
 SHAPES = [(16, 10, 10), (128, 128, 64), (512, 784, 512), (4096, 512, 784), (512, 784, 4096), (257, 67, 130),
           (10, 512, 512), (512, 10, 512), (64, 64, 16), (300, 1000, 500), (1024, 1024, 8), (96, 200, 1000)]

@@ -80,7 +80,7 @@ def test_engines_agree_on_the_mlp_config():
             out[engine, curv] = (prob.gradient(), prob.mvp(v), prob.fisher_diag())
     for curv in ("ggn", "hessian"):
         for a, b in zip(out["tc", curv], out["simt", curv]):
-            # 3xTF32 tensor tiles vs FP32 FMA tiles.  With 4096 x 1024 ReLU units a few pre-activations sit within
+            # split-precision tensor tiles vs FP32 FMA tiles.  With 4096 x 1024 ReLU units a few pre-activations sit within
             # rounding of 0 and flip their mask between the engines (as they do between torch-CPU and torch-CUDA);
             # each flip moves single entries by O(1/N), so the bulk is compared in L2 and the tail loosely.
             assert l2rel(a, b) < 1e-4 and rel(a, b) < 5e-3
