@@ -101,6 +101,12 @@ size_t hf_pcg_state_bytes(int64_t max_iter);
 /* byte offset, inside the state block, of the double array m_0..m_iter (cg.py:189, :97): the values of the
  * quadratic 0.5 x^T A x - b^T x, rounded to the solve dtype like the reference's               */
 size_t hf_pcg_m_iters_offset(void);
+/* Optional progress mirror: `mapped_host_pair` points at two int32 in pinned (device-mapped) host memory; after every
+ * hf_pcg_init / hf_pcg_iter that changes the status the kernel stores {iter, reason} there (iter first), so the host
+ * can follow the solve by reading memory -- no copy, no event, no synchronisation (the reference instead synchronises
+ * >= 4 times per iteration: cg.py:102, :110, :114, :133).  Call before hf_pcg_init on a zeroed state block; NULL
+ * detaches.  The pinned pair must outlive every launch that uses the state block.                               */
+int hf_pcg_set_progress(void* d_state, int32_t* mapped_host_pair, void* stream);
 
 /* Host-visible mirror of the head of the state block (copy sizeof(hf_pcg_status) bytes D2H). */
 typedef struct {

@@ -62,6 +62,7 @@ SIGNATURES = {
     "hf_debug_tc_trace": (C.c_int, [_vp]),
     "hf_pcg_state_bytes": (_sz, [_i64]),
     "hf_pcg_m_iters_offset": (_sz, []),
+    "hf_pcg_set_progress": (C.c_int, [_vp, _vp, _vp]),
     "hf_pcg_init": (C.c_int, [C.c_int, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _i64, C.c_int, C.c_int,
                               _vp, _vp, _vp, _vp]),
     "hf_pcg_iter": (C.c_int, [C.c_int, _i64, _vp, C.c_int, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -19,6 +19,7 @@ How ``M`` is applied:
   ``M=identity`` give bit-identical iterates (reference ``tests/test_cg.py:217``).
 """
 import ctypes as C
+import time
 from math import ceil, log
 from warnings import warn
 
@@ -73,6 +74,25 @@ class _Solver:
         self.x, self.r, self.p = (torch.empty_like(b) for _ in range(3))
         self._host = torch.empty(C.sizeof(PcgStatus), dtype=torch.uint8).pin_memory()
         self._m_off = self.lib.hf_pcg_m_iters_offset()
+        # {iter, reason} published by the kernels into pinned host memory: the host follows the solve by reading it
+        self._progress = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.progress = self._progress.numpy()
+        _lib.check(self.lib.hf_pcg_set_progress(self.state.data_ptr(), self._progress.data_ptr(), _lib.stream()))
+
+    def wait_for(self, iteration, timeout=60.0):
+        """Spin (no CUDA call) until the device has finished ``iteration`` or stopped; returns (iter, reason)."""
+        t0 = None
+        while True:
+            reason = int(self.progress[1])  # reason first: a non-zero reason makes the iter read below final
+            done = int(self.progress[0])
+            if reason != 0 or done >= iteration:
+                return done, reason
+            if t0 is None:
+                t0 = time.perf_counter()
+            elif time.perf_counter() - t0 > timeout:
+                torch.cuda.current_stream().synchronize()  # surfaces a CUDA error if that is why nothing moves
+                if int(self.progress[1]) == 0 and int(self.progress[0]) < iteration:
+                    raise RuntimeError("pcg: the device made no progress (were the iterations enqueued?)")
 
     def init(self, Bx0, x0, minv, lam, tol, atol, martens, split):
         _lib.check(self.lib.hf_pcg_init(
@@ -191,16 +211,20 @@ def cg(
 
 
 def pcg_device(matvec, b, x0=None, minv=None, damping=0.0, max_iter=250, tol=1e-5, atol=None,
-               martens_conv_crit=True, store_x_at_iters=None, poll=8, verbose=False, use_graph=False):
+               martens_conv_crit=True, store_x_at_iters=None, poll=3, verbose=False, use_graph=False):
     """The same solve with a device-resident operator and **no host synchronisation per iteration**.
 
     ``matvec(v, out, skip_ptr)`` enqueues ``out = B v`` (the undamped curvature product) on the current
     stream; the damping ``lambda v`` is added inside the fused kernel (reference ``optimizer.py:266``) and
     ``minv`` (or None) is the hoisted diagonal preconditioner.  Termination is decided on the device
-    (same tests, same order as ``cg.py:96-115``); the host enqueues ``poll`` iterations at a time and
-    looks at the status of the *previous* batch, so the queue never drains.  Launches enqueued after the
-    solver stopped are no-ops (``skip_ptr``), and the iterate/iteration count reported are exactly the
-    ones the reference would stop at.  Returns ``(x_iters, m_iters, reason)`` like :func:`cg`.
+    (same tests, same order as ``cg.py:96-115``) and published as an ``{iter, reason}`` pair in pinned host memory
+    (``hf_pcg_set_progress``).  The host enqueues iteration ``i`` once it knows that iteration ``i - poll`` did not
+    terminate the solve -- a plain memory read, no copy, event or synchronisation -- so the queue holds ``poll - 1``
+    iterations of work beyond the one executing and never drains.  The at most ``poll - 1`` launches enqueued after
+    the solver stopped are no-ops (``skip_ptr``), and the iterate/iteration count reported are exactly the ones the
+    reference would stop at.  The number of enqueued iterations, ``min(max_iter, n_stop + poll - 1)``, does not
+    depend on timing, so data-parallel replicas issue the same collectives.  Returns ``(x_iters, m_iters, reason)``
+    like :func:`cg`.
 
     With ``use_graph`` the body of one iteration (every kernel of the product + the fused update) is captured once
     into a CUDA graph after the first iteration and replayed, which removes the per-launch host cost; ``matvec``
@@ -225,47 +249,39 @@ def pcg_device(matvec, b, x0=None, minv=None, damping=0.0, max_iter=250, tol=1e-
     row = (b.numel() + 3) // 4 * 4  # keep every snapshot row 16-byte aligned
     snaps = torch.empty((max(1, len(slots)), row), dtype=b.dtype, device=b.device)[:, : b.numel()]
 
-    hosts = [torch.empty(C.sizeof(PcgStatus), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    events = [torch.cuda.Event() for _ in range(2)]
-    head = s.state[: hosts[0].numel()]
-    it, batch, stopped = 0, 0, False
+    it, depth = 0, max(1, int(poll))
     graph = None
 
     def one_iteration(snapshot):
         matvec(s.p, Bp, s.reason_ptr)
         s.iterate(PCG_FUSED, Bp=Bp, minv=minv, lam=damping, snapshot=snapshot)
 
-    while it < max_iter and not stopped:
-        for _ in range(poll):
-            it += 1
-            snap = snaps[slots[it]] if it in slots else None
-            if graph is None:
-                one_iteration(snap)
-                if use_graph and it == 1 and max_iter > 2:  # everything lazily initialised: capture the body once
-                    try:
-                        cand, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
-                        side.wait_stream(torch.cuda.current_stream())
-                        with torch.cuda.stream(side):  # bare capture: no gc / empty_cache / device sync
-                            cand.capture_begin()
-                            one_iteration(None)
-                            cand.capture_end()
-                        torch.cuda.current_stream().wait_stream(side)
-                        graph = cand
-                    except Exception:  # noqa: BLE001 -- any capture problem: keep launching directly
-                        graph, use_graph = None, False
-                        torch.cuda.synchronize()
-            else:
-                graph.replay()
-                if snap is not None:
-                    snap.copy_(s.x)  # a terminated solve leaves x untouched, so a late copy is harmless
-            if it == max_iter:
+    while it < max_iter:
+        if it + 1 - depth >= 1:
+            done, reason = s.wait_for(it + 1 - depth)
+            if reason != 0 and done <= it + 1 - depth:
                 break
-        hosts[batch & 1].copy_(head, non_blocking=True)
-        events[batch & 1].record()
-        if batch > 0:  # look at the previous batch while this one runs
-            events[(batch - 1) & 1].synchronize()
-            stopped = PcgStatus.from_buffer_copy(hosts[(batch - 1) & 1].numpy().tobytes()).reason != 0
-        batch += 1
+        it += 1
+        snap = snaps[slots[it]] if it in slots else None
+        if graph is None:
+            one_iteration(snap)
+            if use_graph and it == 1 and max_iter > 2:  # everything lazily initialised: capture the body once
+                try:
+                    cand, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):  # bare capture: no gc / empty_cache / device sync
+                        cand.capture_begin()
+                        one_iteration(None)
+                        cand.capture_end()
+                    torch.cuda.current_stream().wait_stream(side)
+                    graph = cand
+                except Exception:  # noqa: BLE001 -- any capture problem: keep launching directly
+                    graph, use_graph = None, False
+                    torch.cuda.synchronize()
+        else:
+            graph.replay()
+            if snap is not None:
+                snap.copy_(s.x)  # a terminated solve leaves x untouched, so a late copy is harmless
     st = s.status()
     if st.reason == 0:
         raise RuntimeError("pcg_device: solver did not terminate (internal error)")

@@ -22,12 +22,24 @@ struct PcgState {
   int32_t first_beta;  // split-mode init done, p = -y still pending
   int32_t martens;
   int64_t max_iter;
+  int32_t* progress;  // optional host-mapped {iter, reason} pair (hf_pcg_set_progress), written after every update
   // grid all-reduce slots: [0] p.Ap  [1] r.r,(r-b).x,r.y  [2] r.y of a BETA-only launch  [3] start-up sums
   ReduceSlot slots[4][kMaxCtas];
   double m_iters[2];  // really max_iter + 2 entries
 };
 
 constexpr int kThreads = 1024;
+
+// Publish {iter, reason} to pinned host memory so the host can follow the solve without a copy or a sync.  iter is
+// written (and made visible system-wide) before reason: a host that reads reason != 0 first and iter second sees the
+// final iteration count.
+__device__ __forceinline__ void publish_progress(const PcgState* s, int iter, int reason) {
+  volatile int32_t* m = s->progress;
+  if (!m) return;
+  m[0] = iter;
+  __threadfence_system();
+  m[1] = reason;
+}
 
 // optional phase trace (tools/pcg_trace.py): per CTA, %globaltimer at the phase boundaries of pcg_iter_kernel
 __device__ unsigned long long* g_pcg_trace = nullptr;
@@ -245,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_iter_kernel(IterArgs<T> a) {
         s->st.nonpos_pAp = pAp;
       }
       s->st.reason = reason;
+      publish_progress(s, iter, reason);
     }
     if (reason != HF_CG_RUNNING || !want_y) return;
   } else {
@@ -403,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_init_kernel(InitArgs<T> a) {
     s->martens = a.martens;
     s->max_iter = a.max_iter;
     s->m_iters[0] = (double)m0;
+    publish_progress(s, 0, HF_CG_RUNNING);
   }
 }
 
@@ -517,6 +531,14 @@ size_t hf_pcg_state_bytes(int64_t max_iter) {
 }
 
 size_t hf_pcg_m_iters_offset(void) { return offsetof(PcgState, m_iters); }
+
+int hf_pcg_set_progress(void* d_state, int32_t* mapped_host_pair, void* stream) {
+  HF_REQUIRE(d_state, HF_ERR_INVALID, "hf_pcg_set_progress: null state");
+  // pageable source: the runtime stages the 8 bytes before returning, so the local may go out of scope
+  HF_CUDA(cudaMemcpyAsync(static_cast<char*>(d_state) + offsetof(PcgState, progress), &mapped_host_pair,
+                          sizeof(mapped_host_pair), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return HF_OK;
+}
 
 int hf_debug_pcg_trace(void* d_buf) {
   unsigned long long* p = static_cast<unsigned long long*>(d_buf);
