@@ -305,6 +305,42 @@ static __global__ void reduce_partials2_kernel(const float* __restrict__ partW, 
   }
 }
 
+// The same reduction for MANY partial sets of a SHORT vector (the fused head leaves one set per CTA): 8 groups of
+// splits per element run in parallel (z = g, g + 8, ...) and are combined in fixed order, so the chain of dependent
+// loads is splits / 8 long instead of splits.
+static __global__ void __launch_bounds__(256) reduce_tall_kernel(const float* __restrict__ partW, int splitsW, int64_t countW,
+                                                                 float* __restrict__ outW, const float* __restrict__ partB,
+                                                                 int splitsB, int64_t countB, float* __restrict__ outB,
+                                                                 float scale, int accumulate, const int32_t* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ float sm[8][33];
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t total = countW + countB;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + e;
+    const bool w = i < countW;
+    const int64_t j = w ? i : i - countW;
+    float s = 0.f;
+    if (i < total) {
+      const float* part = w ? partW : partB;
+      const int64_t stride = w ? countW : countB;
+      const int splits = w ? splitsW : splitsB;
+#pragma unroll 4
+      for (int z = g; z < splits; z += 8) s += part[(int64_t)z * stride + j];
+    }
+    sm[g][e] = s;
+    __syncthreads();
+    if (g == 0 && i < total) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sm[k][e];
+      float* out = w ? outW : outB;
+      out[j] = (accumulate ? out[j] : 0.f) + scale * t;
+    }
+    __syncthreads();
+  }
+}
+
 // part[z][c] = sum over the z-th row range of d[n][c] (optionally squared): bias gradients
 static __global__ void colsum_kernel(const float* __restrict__ d, int64_t rows, int cols, int64_t ld, int rows_per_split,
                               int square, float* __restrict__ part, const int32_t* __restrict__ skip) {

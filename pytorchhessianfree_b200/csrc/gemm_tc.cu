@@ -43,18 +43,22 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 
 // optional phase trace (tools/tc_trace.py): per CTA, %globaltimer at [0] entry [1] prologue done [2] first stage landed
 // [3] accumulator complete [4] epilogue done
+// consecutive traced launches write consecutive blocks of the buffer (g_tc_epoch, bumped by the host per launch), so
+// the gap between two kernels of a chain can be read off as well
 __device__ unsigned long long* g_tc_trace = nullptr;
-__device__ __forceinline__ void tc_mark(int slot, bool who) {
+__device__ __forceinline__ void tc_mark(int slot, bool who, int epoch = 0) {
   if (g_tc_trace && who) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_tc_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    g_tc_trace[((size_t)epoch * 1024 + cta) * 8 + slot] = t;  // 1024 CTA records per traced launch
   }
 }
 
 struct TcArgs {
   GemmArgs g;
   int a_mn[2], b_mn[2];  // 1 = operand is MN-contiguous in global memory (MN-major UMMA operand)
+  int trace_epoch;       // block of the trace buffer this launch writes (0 unless tracing)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -366,7 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  tc_mark(0, threadIdx.x == 0);
+  tc_mark(0, threadIdx.x == 0, p.trace_epoch);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
@@ -390,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  tc_mark(1, threadIdx.x == 0);
+  tc_mark(1, threadIdx.x == 0, p.trace_epoch);
 
   if (warp == 4) {
     // ---------------- TMA producer ----------------
@@ -453,7 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int it = 0; it < total; ++it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(&full_raw[s], ph);
-      if (it == 0) tc_mark(2, threadIdx.x == 0);
+      if (it == 0) tc_mark(2, threadIdx.x == 0, p.trace_epoch);
       const uint32_t st = smem_u32(tiles + s * STAGE_BYTES);
       if (p.a_mn[sp_pr]) split_tile<true>(st, st + 2 * TILE_BYTES, st + 2 * TILE_BYTES + TILE_BYTES / 2);
       else split_tile<false>(st, st + 2 * TILE_BYTES, st + 2 * TILE_BYTES + TILE_BYTES / 2);
@@ -471,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(acc_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    tc_mark(3, threadIdx.x == 0);
+    tc_mark(3, threadIdx.x == 0, p.trace_epoch);
     constexpr int LDS_ROW = BN + 4;
     const uint32_t stage = smem_u32(tiles) + warp * 32 * LDS_ROW * 4;
 #pragma unroll 2
@@ -488,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + (lane * LDS_ROW + c + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
     }
     __syncwarp();
-    tc_mark(5, threadIdx.x == 0);
+    tc_mark(5, threadIdx.x == 0, p.trace_epoch);
     float cs[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of what this lane stores (bias gradient of the next layer)
     epilogue_dispatch(g, stage, m0 + warp * 32, n0 + lane * 4, lane, cs);
     if (g.colpart) {
@@ -509,7 +513,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  tc_mark(4, threadIdx.x == 0);
+  tc_mark(4, threadIdx.x == 0, p.trace_epoch);
   if (warp == 5) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
   }
@@ -571,7 +575,9 @@ static int make_map(CUtensorMap* map, const Operand& op, int MN, int K) {
   return HF_OK;
 }
 
+static int g_trace_launches = -1;  // >= 0 while tracing: index of the next traced launch
 int set_tc_trace(void* d_buf) {
+  g_trace_launches = d_buf ? 0 : -1;
   unsigned long long* p = static_cast<unsigned long long*>(d_buf);
   HF_CUDA(cudaMemcpyToSymbol(g_tc_trace, &p, sizeof(p)));
   return HF_OK;
@@ -581,6 +587,7 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t stream) {
   HF_REQUIRE(tc_supported(g_in), HF_ERR_UNSUPPORTED, "tcgen05 engine: unsupported shape or alignment");
   TcArgs p;
   p.g = g_in;
+  p.trace_epoch = g_trace_launches >= 0 ? g_trace_launches++ : 0;
   GemmArgs& g = p.g;
   if (g.split_k < 1) g.split_k = 1;
   if (g.split_k == 1) g.k_per_split = ((g.K + BKT - 1) / BKT) * BKT;

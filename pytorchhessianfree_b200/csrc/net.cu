@@ -17,6 +17,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "head.cuh"
 
 namespace hf {
 
@@ -56,6 +57,12 @@ struct hf_lin {
   int fwd_splits_max;
   float* partial;             // split-K partial tiles
   size_t partial_floats;
+  bool head_ok;               // the fused output head (head.cuh) applies to GGN products of this linearisation
+  hf::HeadPlan head;
+  float* head_partW;          // [head.ctas][C*D]
+  float* head_partB;          // [head.ctas][C]
+  float* partial_main;        // second set for the first trainable layer, whose gradient runs on the caller's stream
+  size_t partial_main_floats;
   int fwd_splits;             // > 0: the last rop_forward left split partials in partial_fwd
   const float* fwd_bias;
   std::vector<float*> cot;    // cot[l]: cotangent dloss/dz_l (or its R-derivative) of the sweep in flight
@@ -332,16 +339,18 @@ static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream, b
 // both partial sets in fixed order (deterministic) into the flat vector.
 static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
                           float* out_w, const float* d, int ld_d, int col_tiles, float* colbuf, float* out_b, float scale,
-                          int accumulate, const int32_t* skip, cudaStream_t stream) {
+                          int accumulate, const int32_t* skip, cudaStream_t stream, bool main_scratch = false) {
   int splits_w = 0, splits_b = 0;
+  float* const partial = main_scratch ? lin->partial_main : lin->partial;
   if (out_w) {
     const SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, square));
-    HF_REQUIRE((size_t)sp.splits * M * N <= lin->partial_floats, HF_ERR_WORKSPACE, "split-K scratch too small");
+    HF_REQUIRE((size_t)sp.splits * M * N <= (main_scratch ? lin->partial_main_floats : lin->partial_floats), HF_ERR_WORKSPACE,
+               "split-K scratch too small");
     GemmArgs g = blank_gemm();
     g.M = M, g.N = N, g.K = (int)lin->N, g.n_pairs = n_pairs;
     for (int s = 0; s < n_pairs; ++s) g.A[s] = A[s], g.B[s] = B[s];
     g.square = square;
-    g.C = lin->partial, g.ldc = N;
+    g.C = partial, g.ldc = N;
     g.epi = EPI_STORE;
     g.split_k = sp.splits, g.k_per_split = sp.k_per_split;
     g.skip = skip;
@@ -365,7 +374,7 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
   if (count_w + count_b == 0) return HF_OK;
   int64_t blocks = (count_w / 4 + count_b + 255) / 256 + 1;
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-  reduce_partials2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, splits_w, count_w, out_w, colbuf, splits_b,
+  reduce_partials2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, splits_w, count_w, out_w, colbuf, splits_b,
                                                                count_b, out_b, scale, accumulate, skip);
   HF_LAUNCH_CHECK();
   return HF_OK;
@@ -378,18 +387,20 @@ static float loss_scale(const hf_net* net, int64_t n_total) {
 }
 
 // R-op forward: R{output} = J v into lin->buf[which]; returns the buffer index holding it
+// (with `below_head` the last layer is left to the fused head and *below_head receives R{a_{L-2}})
 static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hessian, const int32_t* skip,
-                       cudaStream_t stream, int* out_buf) {
+                       cudaStream_t stream, int* out_buf, const float** below_head = nullptr) {
   const hf_net* net = lin->net;
   const int nl = (int)net->L.size();
+  const int l_end = nl - (below_head ? 1 : 0);
   const float* cur = nullptr;
   int which = 0;
-  for (int l = net->first_trainable; l < nl; ++l)
+  for (int l = net->first_trainable; l < l_end; ++l)
     if (lin->vpad[l]) {
       int rc = pitch_rows(v + net->L[l].w_off, lin->vpad[l], net->L[l].out, net->L[l].in, skip, stream);
       if (rc) return rc;
     }
-  for (int l = net->first_trainable; l < nl; ++l) {
+  for (int l = net->first_trainable; l < l_end; ++l) {
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
     const int ld_in = l == 0 ? L.in : pad4(L.in), ld_out = pad4(L.out);
@@ -446,6 +457,7 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
   }
   // cur is the last layer's output tangent and lives in a ping-pong buffer
   *out_buf = (cur == lin->buf[0]) ? 0 : 1;
+  if (below_head) *below_head = cur;
   return HF_OK;
 }
 
@@ -465,6 +477,31 @@ static int apply_loss_hessian(hf_lin* lin, float* rz, const int32_t* skip, cudaS
   return HF_OK;
 }
 
+// Fused output head (head.cuh): R-op through the last layer, loss Hessian, transposed product down to cot[L-2] and the
+// per-CTA partials of the head's own gradient slices, in one launch.  `ra` = R{a_{L-2}} from rop_forward.
+static int ggn_head(hf_lin* lin, const float* theta, const float* v, const float* ra, const int32_t* skip,
+                    cudaStream_t stream) {
+  const hf_net* net = lin->net;
+  const int nl = (int)net->L.size();
+  const Layer& L = net->L[nl - 1];
+  const Layer& Lp = net->L[nl - 2];
+  HeadArgs h;
+  h.a = lin->a[nl - 2], h.ra = ra;
+  h.W = theta + L.w_off, h.V = v + L.w_off;
+  h.vb = (L.has_bias && L.b_off >= 0) ? v + L.b_off : nullptr;
+  h.prob = net->loss == HF_LOSS_MSE ? nullptr : lin->prob;
+  h.cot = lin->cot[nl - 2];
+  h.partW = lin->head_partW;
+  h.partB = (L.has_bias && L.b_off >= 0) ? lin->head_partB : nullptr;
+  h.partCol = (Lp.has_bias && Lp.b_off >= 0) ? lin->colbuf[nl - 2] : nullptr;
+  h.N = lin->N, h.D = L.in, h.Dp = lin->head.Dp, h.C = L.out, h.ld = pad4(L.in), h.ldc = pad4(L.out);
+  h.loss = net->loss, h.act_prev = Lp.act;
+  h.scale = loss_scale(net, lin->n_total);
+  h.rows_per_cta = lin->head.rows_per_cta;
+  h.skip = skip;
+  return launch_head(h, lin->head, stream);
+}
+
 enum BackMode { BACK_GRADIENT, BACK_GGN, BACK_FISHER, BACK_HESSIAN };
 
 // Transposed sweep from the output signal `top` ([N,C]) down to the first trainable layer.
@@ -476,7 +513,7 @@ enum BackMode { BACK_GRADIENT, BACK_GGN, BACK_FISHER, BACK_HESSIAN };
 // cotangent is left in lin->pending_cur).  phase 1: only that gradient.  The split lets a data-parallel caller start
 // the all-reduce of the upper layers' slices while the (largest, last) first-layer gradient is still being formed.
 static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const float* top, float* out, int accumulate,
-                          BackMode mode, const int32_t* skip, cudaStream_t stream, int phase = -1) {
+                          BackMode mode, const int32_t* skip, cudaStream_t stream, int phase = -1, bool head = false) {
   const hf_net* net = lin->net;
   const int nl = (int)net->L.size();
   const bool keep = mode == BACK_GRADIENT && (lin->flags & HF_LIN_HESSIAN);
@@ -498,6 +535,24 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       lin->pending_cur = cur, lin->pending_cols = cur_col_tiles;
       break;
     }
+    if (head && l == nl - 1) {
+      // the fused head already produced cot[l-1] (+ its column sums) and the partials of this layer's own slices
+      const Layer& Lh = net->L[l];
+      const bool has_b = Lh.has_bias && Lh.b_off >= 0;
+      if (fork) HF_CUDA(cudaStreamWaitEvent(gstream, lin->ev[l], 0));
+      const int64_t count_w = (int64_t)Lh.out * Lh.in, count_b = has_b ? Lh.out : 0;
+      int64_t blocks = (count_w + count_b + 31) / 32;
+      if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+      reduce_tall_kernel<<<(unsigned)blocks, 256, 0, gstream>>>(lin->head_partW, lin->head.ctas, count_w, out + Lh.w_off,
+                                                               lin->head_partB, lin->head.ctas, count_b,
+                                                               has_b ? out + Lh.b_off : nullptr, scale, accumulate, skip);
+      HF_LAUNCH_CHECK();
+      if (fork) HF_CUDA(cudaEventRecord(lin->ev[l - 1], stream));
+      const Layer& Lp = net->L[l - 1];
+      cur = lin->cot[l - 1];
+      cur_col_tiles = (Lp.has_bias && Lp.b_off >= 0) ? lin->head.ctas : 0;
+      continue;
+    }
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
     const int ld_in = l == 0 ? L.in : pad4(L.in), ld_out = pad4(L.out);
@@ -509,10 +564,13 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
         A[np] = op_mnc(lin->delta[l], ld_out), B[np] = op_mnc(lin->ra[l - 1], ld_in), ++np;
       }
       const bool has_b = L.has_bias && L.b_off >= 0;
-      if (fork) HF_CUDA(cudaStreamWaitEvent(gstream, lin->ev[l], 0));
+      // The first trainable layer's gradient is the end of the chain: the caller's stream has nothing left to do, so
+      // it runs there (own split-K scratch) while the side stream finishes the upper layers' reductions.
+      const bool on_main = fork && l == net->first_trainable && lin->partial_main != nullptr;
+      if (fork && !on_main) HF_CUDA(cudaStreamWaitEvent(gstream, lin->ev[l], 0));
       int rc = layer_gradient(lin, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
                               cur_col_tiles, lin->colbuf[l], has_b ? out + L.b_off : nullptr, scale, accumulate, skip,
-                              gstream);
+                              on_main ? stream : gstream, on_main);
       if (rc) return rc;
     }
     cur_col_tiles = 0;
@@ -661,6 +719,14 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       pf = std::max(pf, (size_t)colsum_plan(N) * L.out);
     }
   float* part = pf ? (float*)take(sizeof(float) * pf) : nullptr;
+  size_t pf_main = 0;
+  if (!loss_only && net->L[net->first_trainable].w_off >= 0 && net->first_trainable < nl - 1) {
+    const Layer& L = net->L[net->first_trainable];
+    const int splits = std::max(plan_split(L.out, L.in, N, false).splits,
+                                weight_on_tensor(net, L.out, L.in, N, 0) ? plan_split(L.out, L.in, N, true).splits : 1);
+    pf_main = (size_t)splits * L.out * L.in;
+  }
+  float* part_main = pf_main ? (float*)take(sizeof(float) * pf_main) : nullptr;
   const int fwd_max = (!loss_only && net->classes <= 32) ? 16 : 0;
   float* pfwd = fwd_max ? (float*)take(sizeof(float) * fwd_max * N * pad4(net->classes)) : nullptr;
   if (lin) lin->partial_fwd = pfwd, lin->fwd_splits_max = fwd_max, lin->fwd_splits = 0, lin->fwd_bias = nullptr;
@@ -676,7 +742,18 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       float* vp = L.w_off >= 0 ? (float*)take(sizeof(float) * L.out * pad4(L.in)) : nullptr;
       if (lin) lin->wpad[l] = wp, lin->vpad[l] = vp;
     }
-  const size_t col_rows = (size_t)std::max<int64_t>(colsum_plan(N), (N + 127) / 128);
+  // fused output head for GGN products: narrow trainable last layer without activation on top of a trainable stack
+  bool head_ok = false;
+  HeadPlan hp = {};
+  if (!loss_only && nl >= 2 && net->first_trainable < nl - 1) {
+    const Layer& Lh = net->L[nl - 1];
+    head_ok = Lh.act == HF_ACT_NONE && Lh.w_off >= 0 && head_shape_ok(N, Lh.in, Lh.out, sm_count());
+    if (head_ok) hp = head_plan(N, Lh.in, Lh.out, sm_count());
+  }
+  float* hpw = head_ok ? (float*)take(sizeof(float) * (size_t)hp.ctas * net->L[nl - 1].out * net->L[nl - 1].in) : nullptr;
+  float* hpb = head_ok ? (float*)take(sizeof(float) * (size_t)hp.ctas * net->L[nl - 1].out) : nullptr;
+  if (lin) lin->head_ok = head_ok, lin->head = hp, lin->head_partW = hpw, lin->head_partB = hpb;
+  const size_t col_rows = (size_t)std::max<int64_t>(std::max<int64_t>(colsum_plan(N), (N + 127) / 128), head_ok ? hp.ctas : 0);
   if (lin) lin->cot.assign(nl, nullptr), lin->colbuf.assign(nl, nullptr), lin->col_rows = col_rows;
   if (!loss_only)
     for (int l = net->first_trainable; l < nl; ++l) {
@@ -700,7 +777,8 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   }
   if (lin) {
     lin->prob = prob, lin->deltaL = dL, lin->buf[0] = b0, lin->buf[1] = b1;
-    lin->partial = part, lin->partial_floats = pf, lin->loss_partial = lp, lin->loss_blocks = (int)lb;
+    lin->partial = part, lin->partial_floats = pf, lin->partial_main = part_main, lin->partial_main_floats = pf_main;
+    lin->loss_partial = lp, lin->loss_blocks = (int)lb;
   }
   return off;
 }
@@ -818,6 +896,14 @@ int hf_ggn_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, float* 
   HF_REQUIRE(d_v && d_out, HF_ERR_INVALID, "hf_ggn_matvec: null vector");
   cudaStream_t stream = (cudaStream_t)stream_;
   int top = 0;
+  if (lin->head_ok) {
+    const float* ra = nullptr;
+    rc = rop_forward(lin, d_theta, d_v, false, d_skip, stream, &top, &ra);
+    if (rc) return rc;
+    rc = ggn_head(lin, d_theta, d_v, ra, d_skip, stream);
+    if (rc) return rc;
+    return backward_sweep(lin, d_theta, d_v, nullptr, d_out, accumulate, BACK_GGN, d_skip, stream, -1, true);
+  }
   rc = rop_forward(lin, d_theta, d_v, false, d_skip, stream, &top);
   if (rc) return rc;
   rc = apply_loss_hessian(lin, lin->buf[top], d_skip, stream);
@@ -836,6 +922,14 @@ int hf_matvec_phase(hf_lin_t* lin, int32_t kind, const float* d_theta, const flo
   const BackMode mode = kind == 1 ? BACK_HESSIAN : BACK_GGN;
   if (phase == 0) {
     int top = 0;
+    if (kind == 0 && lin->head_ok) {
+      const float* ra = nullptr;
+      rc = rop_forward(lin, d_theta, d_v, false, d_skip, stream, &top, &ra);
+      if (rc) return rc;
+      rc = ggn_head(lin, d_theta, d_v, ra, d_skip, stream);
+      if (rc) return rc;
+      return backward_sweep(lin, d_theta, d_v, nullptr, d_out, accumulate, mode, d_skip, stream, 0, true);
+    }
     rc = rop_forward(lin, d_theta, d_v, kind == 1, d_skip, stream, &top);
     if (rc) return rc;
     rc = apply_loss_hessian(lin, lin->buf[top], d_skip, stream);
