@@ -8,6 +8,8 @@ every rank needs :func:`global_count` before it scales its local sums (reference
 """
 import torch
 
+from . import nccl_direct as _nccl_direct
+
 
 def world(group=None):
     """(rank, world_size) of ``group``; (0, 1) when torch.distributed is not initialised."""
@@ -30,7 +32,13 @@ def all_reduce_sum(t, group=None):
     if group is not None:
         import torch.distributed as dist
 
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        comm = None
+        if t.is_cuda and t.is_contiguous() and t.dtype in _nccl_direct._DTYPES:
+            comm = _nccl_direct.comm_for(group)
+        if comm is not None:
+            comm.all_reduce_sum(t)  # same collective, enqueued on the launching stream (see nccl_direct.py)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
 
 
