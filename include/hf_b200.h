@@ -76,6 +76,9 @@ int hf_debug_pcg_trace(void* d_buf);
 /* same for the tcgen05 contraction kernel: [cta][0] entry, [1] prologue done (barriers, TMEM), [2] first stage landed,
  * [3] accumulator complete, [4] epilogue done (d_buf >= 8 * n_ctas uint64) */
 int hf_debug_tc_trace(void* d_buf);
+/* per-k-block pipeline trace of CTA (0,0,0) of the same kernel, first 64 k-blocks: [it][0] TMA issued, [1] raw tiles seen
+ * by the splitters, [2] split done, [3] MMAs issued, [4] producer's slot wait done (d_buf >= 64 * 8 uint64) */
+int hf_debug_tc_trace_iters(void* d_buf);
 
 /* ------------------------------------------------------------------------------------------
  * Fused PCG vector pass  (cg.py:186-224 + optimizer.py:266 + preconditioners.py:125)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "hf_debug_launch_count": (C.c_longlong, []),
     "hf_debug_pcg_trace": (C.c_int, [_vp]),
     "hf_debug_tc_trace": (C.c_int, [_vp]),
+    "hf_debug_tc_trace_iters": (C.c_int, [_vp]),
     "hf_pcg_state_bytes": (_sz, [_i64]),
     "hf_pcg_m_iters_offset": (_sz, []),
     "hf_pcg_set_progress": (C.c_int, [_vp, _vp, _vp]),
@@ -100,7 +101,7 @@ def load():
             f"{LIB_PATH} is missing: the sm_100a kernels are not built. Run "
             "`python -m pytorchhessianfree_b200.build` (there is no CPU or PyTorch fallback)."
         )
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(os.environ.get("HF_B200_LIB", LIB_PATH))  # override: A/B builds of the same ABI
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args

@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("HF_B200_DEFS", "").split(), "-c", src, "-o", obj]  # e.g. -DHF_TC_ITER_TRACE=1
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -23,10 +23,19 @@
 //   epilogue tcgen05.ld 32x32b -> registers -> the same fused epilogues as the SIMT engine (bias, act', act'', raw
 //            copy, split-K partials) -> global.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm_tc.cuh"
 
 namespace hf {
+
+#ifndef HF_TC_ITER_TRACE
+#define HF_TC_ITER_TRACE 0  // compile with -DHF_TC_ITER_TRACE=1 for tools/tc_pipeline_trace.py (costs ~10 % of the loop)
+#endif
+#ifndef HF_TC_RS1
+#define HF_TC_RS1 4
+#define HF_TC_LS1 2
+#endif
 
 // Tile 128x128, k-block of BKT floats.  BKT = 32: 128-byte swizzle rows, 193 KB of shared memory, one CTA per SM.
 // BKT = 16 (64-byte rows, 97 KB, two CTAs per SM) is supported by every piece below and was measured: the co-resident
@@ -35,11 +44,29 @@ namespace hf {
 constexpr int BM = 128, BN = 128, BKT = 32;
 constexpr int kCtasPerSm = BKT == 32 ? 1 : 2;
 constexpr uint32_t kKMajorLayout = BKT == 32 ? 2u : 4u;  // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BKT * 4;                  // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;               // rawA | rawB | loA | loB
+constexpr int TILE_BYTES = BM * BKT * 4;                  // 16 KB per 128-row FP32 operand tile
 constexpr int TC_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// NCTA = 1: one CTA per tile.  NCTA = 2: a CTA pair (cluster of two along M, tcgen05 cta_group::2) computes two
+// vertically adjacent tiles with one M = 256 MMA: each CTA stages its own A tile and HALF of the shared B tile, so
+// per k-block a CTA moves 120 KB instead of 160 KB through its shared memory (the main loop's bound) and the
+// smaller stages make room for a fourth ring slot.
+template <int NCTA>
+struct TcCfg {
+  // Two rings with their own barriers: raw FP32 tiles (TMA -> splitters + TF32 MMAs) and BF16 tiles (splitters ->
+  // BF16 MMAs).  Depths measured on B200 (us per k-block, M=4096 N=512 K=2048): 4 raw + 2 BF16 slots 0.64, 3 + 3
+  // 0.66; issuing the TF32 term of block i ahead of the BF16 terms of block i-1 0.76 (the single issuing thread then
+  // waits on the two rings in a fixed order).
+  static constexpr int RAW_STAGES = NCTA == 1 ? HF_TC_RS1 : 4;
+  static constexpr int LO_STAGES = NCTA == 1 ? HF_TC_LS1 : 4;
+  static constexpr int B_ROWS = BN / NCTA;                     // rows of B this CTA stages
+  static constexpr int B_BYTES = TILE_BYTES / NCTA;
+  static constexpr int OFF_RAW_B = TILE_BYTES;                 // raw slot:  rawA | rawB
+  static constexpr int RAW_BYTES = TILE_BYTES + B_BYTES;       // 32 KB / 24 KB
+  static constexpr int OFF_B16 = TILE_BYTES;                   // BF16 slot: loA16 hiA16 | loB16 hiB16
+  static constexpr int LO_BYTES = TILE_BYTES + B_BYTES;        // 32 KB / 24 KB
+  static constexpr int RING_BYTES = RAW_STAGES * RAW_BYTES + LO_STAGES * LO_BYTES;  // 192 KB
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 // optional phase trace (tools/tc_trace.py): per CTA, %globaltimer at [0] entry [1] prologue done [2] first stage landed
 // [3] accumulator complete [4] epilogue done
@@ -52,6 +79,17 @@ __device__ __forceinline__ void tc_mark(int slot, bool who, int epoch = 0) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     g_tc_trace[((size_t)epoch * 1024 + cta) * 8 + slot] = t;  // 1024 CTA records per traced launch
+  }
+}
+
+// per-k-block pipeline trace of CTA (0,0,0) (tools/tc_pipeline_trace.py): [it][0] TMA issued [1] raw seen by the
+// splitters [2] split done [3] MMAs issued [4] slot wait of the producer done
+__device__ unsigned long long* g_tc_trace_it = nullptr;
+__device__ __forceinline__ void tc_mark_it(unsigned long long* buf, int slot, int it) {  // buf: read once per thread
+  if (HF_TC_ITER_TRACE && buf && it < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    buf[it * 8 + slot] = t;
   }
 }
 
@@ -113,6 +151,55 @@ __device__ __forceinline__ float tf32_round(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// ---- CTA-pair (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -161,7 +248,7 @@ __device__ __forceinline__ uint64_t corr_desc(uint32_t base, int mn_major, int k
 // Splitter: one FP32 operand tile (in its UMMA/TMA swizzled layout) -> two BF16 tiles of the same major-ness:
 // hi16 = bf16(x) and lo16 = bf16(x - trunc_tf32(x)).  The FP32 tile is element (row, k-quad) addressed by undoing the
 // TMA swizzle; the BF16 tiles are written in the canonical UMMA layout for 16-bit operands.
-template <bool MN>
+template <bool MN, int ROWS>
 __device__ __forceinline__ void split_tile(uint32_t src, uint32_t lo16, uint32_t hi16) {  // shared-space addresses
   // element i = tid + 128 t (t = 0..7) of the FP32 tile is the float4 at src + 16 i; all swizzle arithmetic depends on
   // tid only and is hoisted, the t-dependence is a compile-time constant
@@ -175,12 +262,13 @@ __device__ __forceinline__ void split_tile(uint32_t src, uint32_t lo16, uint32_t
     const int m0 = (((pc >> 1) ^ r0) & 3) * 8 + (pc & 1) * 4;
     off0 = r0 * 128 + ((((m0 >> 3) ^ r0) & 7) << 4) + ((m0 & 4) << 1);
   }
-  float4 v[8];
+  constexpr int NT = ROWS / 16;  // float4 per thread: ROWS x 8 quads over 128 threads
+  float4 v[NT];
 #pragma unroll
-  for (int t = 0; t < 8; ++t)
+  for (int t = 0; t < NT; ++t)
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[t].x), "=f"(v[t].y), "=f"(v[t].z), "=f"(v[t].w) : "r"(src + 16 * tid + 2048 * t));
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < NT; ++t) {
     const float lx = v[t].x - __uint_as_float(__float_as_uint(v[t].x) & 0xffffe000u);
     const float ly = v[t].y - __uint_as_float(__float_as_uint(v[t].y) & 0xffffe000u);
     const float lz = v[t].z - __uint_as_float(__float_as_uint(v[t].z) & 0xffffe000u);
@@ -355,43 +443,63 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, uint32_t st
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, kCtasPerSm)
+template <int NCTA>
+__global__ void __launch_bounds__(TC_THREADS, NCTA == 1 ? kCtasPerSm : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ TcArgs p) {
+  using Cfg = TcCfg<NCTA>;
+  constexpr int RS = Cfg::RAW_STAGES, LS = Cfg::LO_STAGES;
   const GemmArgs& g = p.g;
-  if (g.skip && *g.skip) return;  // uniform: solver already terminated
+  if (g.skip && *g.skip) return;  // uniform (also across a CTA pair): solver already terminated
+  // pair: rank 0 (even tile row) is the leader and issues the M = 256 MMAs for both CTAs
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(tiles + STAGES * STAGE_BYTES);
-  uint64_t* full_raw = bars;              // [STAGES] TMA bytes landed
-  uint64_t* full_lo = bars + STAGES;      // [STAGES] splitters done
-  uint64_t* empty = bars + 2 * STAGES;    // [STAGES] MMAs of the stage retired
-  uint64_t* acc_full = bars + 3 * STAGES; // accumulator complete
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 1);
+  uint8_t* lo_tiles = tiles + RS * Cfg::RAW_BYTES;
+  uint64_t* bars = (uint64_t*)(tiles + Cfg::RING_BYTES);
+  uint64_t* full_raw = bars;                  // [RS] TMA bytes landed
+  uint64_t* empty_raw = bars + RS;            // [RS] MMAs reading the raw slot retired
+  uint64_t* full_lo = bars + 2 * RS;          // [LS] splitters done
+  uint64_t* empty_lo = bars + 2 * RS + LS;    // [LS] MMAs reading the BF16 slot retired
+  uint64_t* acc_full = bars + 2 * RS + 2 * LS; // accumulator complete
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* const trace_it = (HF_TC_ITER_TRACE && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) ? g_tc_trace_it : nullptr;
   tc_mark(0, threadIdx.x == 0, p.trace_epoch);
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // pair: the two CTAs of a cluster must be neighbours in x, so the pair kernel runs tile rows along x
+  const int tile_m = NCTA == 2 ? blockIdx.x : blockIdx.y, tile_n = NCTA == 2 ? blockIdx.y : blockIdx.x;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
+  const int nb0 = n0 + (int)cta_rank * Cfg::B_ROWS;  // first row of B this CTA stages
   const int k_begin = blockIdx.z * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
   const int n_kb = k_end > k_begin ? (k_end - k_begin + BKT - 1) / BKT : 0;
   const int total = n_kb * g.n_pairs;
 
   if (warp == 4 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < RS; ++s) {
       mbar_init(&full_raw[s], 1);
-      mbar_init(&full_lo[s], 4);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty_raw[s], 1);
+    }
+    for (int s = 0; s < LS; ++s) {
+      mbar_init(&full_lo[s], 4 * NCTA);  // the leader's barrier collects the splitter warps of both CTAs
+      mbar_init(&empty_lo[s], 1);
     }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (NCTA == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   tc_mark(1, threadIdx.x == 0, p.trace_epoch);
@@ -400,12 +508,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        const int s = it % RS, ph = (it / RS) & 1;
         const int pr = it / n_kb, k0 = k_begin + (it % n_kb) * BKT;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full_raw[s], 2 * TILE_BYTES);
-        uint8_t* rawA = tiles + s * STAGE_BYTES;
-        uint8_t* rawB = rawA + TILE_BYTES;
+        mbar_wait(&empty_raw[s], ph ^ 1);
+        tc_mark_it(trace_it, 4, it);
+        mbar_expect_tx(&full_raw[s], TILE_BYTES + Cfg::B_BYTES);
+        uint8_t* rawA = tiles + s * Cfg::RAW_BYTES;
+        uint8_t* rawB = rawA + Cfg::OFF_RAW_B;
         const CUtensorMap* ma = pr ? &tmA1 : &tmA0;
         const CUtensorMap* mb = pr ? &tmB1 : &tmB0;
         if (p.a_mn[pr]) {
@@ -416,57 +525,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (p.b_mn[pr]) {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(rawB + j * (BKT * 128), mb, n0 + 32 * j, k0, &full_raw[s]);
+          for (int j = 0; j < Cfg::B_ROWS / 32; ++j) tma_load_2d(rawB + j * (BKT * 128), mb, nb0 + 32 * j, k0, &full_raw[s]);
         } else {
-          tma_load_2d(rawB, mb, k0, n0, &full_raw[s]);
+          tma_load_2d(rawB, mb, k0, nb0, &full_raw[s]);  // box of B_ROWS rows (the B maps are encoded per NCTA)
         }
+        tc_mark_it(trace_it, 0, it);
       }
     }
   } else if (warp == 5) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (pair: the leader CTA only) ----------------
+    if (lane == 0 && cta_rank == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a/b format [7,10)/[10,13) (TF32 = 2,
+      // BF16 = 1), majors 15/16, N>>3 [17,23), M>>4 [24,29)
+      auto idesc_of = [&](int pr, uint32_t fmt) {
+        return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn[pr] << 15) | ((uint32_t)p.b_mn[pr] << 16) |
+               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
+      };
       for (int it = 0; it < total; ++it) {
-        const int s = it % STAGES, ph = (it / STAGES) & 1, pr = it / n_kb;
-        // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a/b=TF32 [7,10)/[10,13), majors 15/16,
-        // N>>3 [17,23), M>>4 [24,29)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn[pr] << 15) |
-                               ((uint32_t)p.b_mn[pr] << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const int s = it % RS, ph = (it / RS) & 1, pr = it / n_kb;
+        const int l = it % LS, phl = (it / LS) & 1;
         mbar_wait(&full_raw[s], ph);
-        mbar_wait(&full_lo[s], ph);
+        // pair: the peer's splitters arrive on the leader's barrier after they saw the peer's own TMA bytes land, so
+        // this wait covers the peer's raw and BF16 tiles as well
+        if (NCTA == 2) mbar_wait_cluster(&full_lo[l], phl);
+        else mbar_wait(&full_lo[l], phl);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t rawA = smem_u32(tiles + s * STAGE_BYTES), rawB = rawA + TILE_BYTES;
+        const uint32_t rawA = smem_u32(tiles + s * Cfg::RAW_BYTES), rawB = rawA + Cfg::OFF_RAW_B;
         // corrections in BF16 (half the tensor time of a TF32 MMA): A_lo*B_hi + A_hi*B_lo with 8-bit operands is
         // 2^-10 * 2^-8 = 2^-18 relative per product, random sign
-        const uint32_t idesc16 = (idesc & ~((7u << 7) | (7u << 10))) | (1u << 7) | (1u << 10);
-        const uint32_t loA = rawA + 2 * TILE_BYTES, hiA = loA + TILE_BYTES / 2, loB = hiA + TILE_BYTES / 2, hiB = loB + TILE_BYTES / 2;
+        const uint32_t idesc = idesc_of(pr, 2u), idesc16 = idesc_of(pr, 1u);
+        const uint32_t loA = smem_u32(lo_tiles + l * Cfg::LO_BYTES), hiA = loA + TILE_BYTES / 2;
+        const uint32_t loB = loA + Cfg::OFF_B16, hiB = loB + Cfg::B_BYTES / 2;
+        if (NCTA == 1) {
 #pragma unroll
-        for (int ks = 0; ks < BKT / 8; ++ks)
-          umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], ks), operand_desc(rawB, p.b_mn[pr], ks), idesc, (it | ks) != 0);
+          for (int ks = 0; ks < BKT / 8; ++ks)
+            umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], ks), operand_desc(rawB, p.b_mn[pr], ks), idesc, (it | ks) != 0);
 #pragma unroll
-        for (int ks = 0; ks < BKT / 16; ++ks) {
-          umma_bf16(tmem_base, corr_desc(loA, p.a_mn[pr], ks), corr_desc(hiB, p.b_mn[pr], ks), idesc16, 1);
-          umma_bf16(tmem_base, corr_desc(hiA, p.a_mn[pr], ks), corr_desc(loB, p.b_mn[pr], ks), idesc16, 1);
+          for (int ks = 0; ks < BKT / 16; ++ks) {
+            umma_bf16(tmem_base, corr_desc(loA, p.a_mn[pr], ks), corr_desc(hiB, p.b_mn[pr], ks), idesc16, 1);
+            umma_bf16(tmem_base, corr_desc(hiA, p.a_mn[pr], ks), corr_desc(loB, p.b_mn[pr], ks), idesc16, 1);
+          }
+          umma_commit(&empty_raw[s]);
+          umma_commit(&empty_lo[l]);
+          tc_mark_it(trace_it, 3, it);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < BKT / 8; ++ks)
+            umma2_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], ks), operand_desc(rawB, p.b_mn[pr], ks), idesc, (it | ks) != 0);
+#pragma unroll
+          for (int ks = 0; ks < BKT / 16; ++ks) {
+            umma2_bf16(tmem_base, corr_desc(loA, p.a_mn[pr], ks), corr_desc(hiB, p.b_mn[pr], ks), idesc16, 1);
+            umma2_bf16(tmem_base, corr_desc(hiA, p.a_mn[pr], ks), corr_desc(loB, p.b_mn[pr], ks), idesc16, 1);
+          }
+          umma2_commit(&empty_raw[s]);  // frees the slots in both CTAs
+          umma2_commit(&empty_lo[l]);
         }
-        umma_commit(&empty[s]);
       }
-      umma_commit(acc_full);
+      if (NCTA == 1) umma_commit(acc_full);
+      else umma2_commit(acc_full);
     }
   } else {
     // ---------------- splitters ----------------
     int sp_pr = 0, sp_kb = 0;
     for (int it = 0; it < total; ++it) {
-      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      const int s = it % RS, ph = (it / RS) & 1;
+      const int l = it % LS, phl = (it / LS) & 1;
+      mbar_wait(&empty_lo[l], phl ^ 1);
       mbar_wait(&full_raw[s], ph);
       if (it == 0) tc_mark(2, threadIdx.x == 0, p.trace_epoch);
-      const uint32_t st = smem_u32(tiles + s * STAGE_BYTES);
-      if (p.a_mn[sp_pr]) split_tile<true>(st, st + 2 * TILE_BYTES, st + 2 * TILE_BYTES + TILE_BYTES / 2);
-      else split_tile<false>(st, st + 2 * TILE_BYTES, st + 2 * TILE_BYTES + TILE_BYTES / 2);
-      if (p.b_mn[sp_pr]) split_tile<true>(st + TILE_BYTES, st + 3 * TILE_BYTES, st + 3 * TILE_BYTES + TILE_BYTES / 2);
-      else split_tile<false>(st + TILE_BYTES, st + 3 * TILE_BYTES, st + 3 * TILE_BYTES + TILE_BYTES / 2);
+      if (threadIdx.x == 0) tc_mark_it(trace_it, 1, it);
+      const uint32_t st = smem_u32(tiles + s * Cfg::RAW_BYTES), lo = smem_u32(lo_tiles + l * Cfg::LO_BYTES);
+      if (p.a_mn[sp_pr]) split_tile<true, BM>(st, lo, lo + TILE_BYTES / 2);
+      else split_tile<false, BM>(st, lo, lo + TILE_BYTES / 2);
+      if (p.b_mn[sp_pr])
+        split_tile<true, Cfg::B_ROWS>(st + Cfg::OFF_RAW_B, lo + Cfg::OFF_B16, lo + Cfg::OFF_B16 + Cfg::B_BYTES / 2);
+      else
+        split_tile<false, Cfg::B_ROWS>(st + Cfg::OFF_RAW_B, lo + Cfg::OFF_B16, lo + Cfg::OFF_B16 + Cfg::B_BYTES / 2);
       if (++sp_kb == n_kb) sp_kb = 0, ++sp_pr;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA unit
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_lo[s]);
+      if (threadIdx.x == 0) tc_mark_it(trace_it, 2, it);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(&full_lo[l], 0);
+        else mbar_arrive(&full_lo[l]);
+      }
     }
     // ---------------- epilogue ----------------
     // TMEM -> registers (one accumulator row per lane) -> shared (the pipeline buffers are idle once acc_full fired)
@@ -506,16 +648,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int e = 0; e < 4; ++e) {
           const int idx = lane * 4 + e;
           const float t = (red[idx] + red[BN + idx]) + (red[2 * BN + idx] + red[3 * BN + idx]);
-          if (n + e < g.N) g.colpart[(int64_t)blockIdx.y * g.N + n + e] = t;
+          if (n + e < g.N) g.colpart[(int64_t)tile_m * g.N + n + e] = t;
         }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair is still in flight
+  else __syncthreads();
   tc_mark(4, threadIdx.x == 0, p.trace_epoch);
   if (warp == 5) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    if (NCTA == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
   }
 }
 
@@ -554,7 +700,7 @@ bool tc_supported(const GemmArgs& g) {
 }
 
 // 2-D tensor map over one operand.  K-contiguous: dims (K, MN), box (32, 128).  MN-contiguous: dims (MN, K), box (32, 32).
-static int make_map(CUtensorMap* map, const Operand& op, int MN, int K) {
+static int make_map(CUtensorMap* map, const Operand& op, int MN, int K, int box_rows = BM) {
   const bool mn_major = op.s_k != 1;
   cuuint64_t dims[2], strides[1];
   cuuint32_t box[2], estr[2] = {1, 1};
@@ -563,7 +709,7 @@ static int make_map(CUtensorMap* map, const Operand& op, int MN, int K) {
     box[0] = 32, box[1] = BKT;
   } else {
     dims[0] = (cuuint64_t)K, dims[1] = (cuuint64_t)MN, strides[0] = (cuuint64_t)op.s_mn * 4;
-    box[0] = BKT, box[1] = BM;
+    box[0] = BKT, box[1] = (cuuint32_t)box_rows;
   }
   CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(op.ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -583,6 +729,12 @@ int set_tc_trace(void* d_buf) {
   return HF_OK;
 }
 
+int set_tc_trace_iters(void* d_buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(d_buf);
+  HF_CUDA(cudaMemcpyToSymbol(g_tc_trace_it, &p, sizeof(p)));
+  return HF_OK;
+}
+
 int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t stream) {
   HF_REQUIRE(tc_supported(g_in), HF_ERR_UNSUPPORTED, "tcgen05 engine: unsupported shape or alignment");
   TcArgs p;
@@ -592,23 +744,49 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t stream) {
   if (g.split_k < 1) g.split_k = 1;
   if (g.split_k == 1) g.k_per_split = ((g.K + BKT - 1) / BKT) * BKT;
   HF_REQUIRE(g.k_per_split % BKT == 0, HF_ERR_INVALID, "tcgen05 engine: K split must be a multiple of %d", BKT);
+  // CTA pairs need an even number of tile rows (a cluster of two along M).  Off unless HF_TC_PAIR=1: parity-green, but
+  // measured slower than single-CTA tiles on B200 (the loop is latency-bound and the pair adds cluster round trips)
+  const dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.split_k);
+  static const bool pair_allowed = getenv("HF_TC_PAIR") && atoi(getenv("HF_TC_PAIR")) != 0;
+  const bool pair = pair_allowed && grid.y % 2 == 0;
   CUtensorMap maps[4];
   for (int s = 0; s < 2; ++s) {
     const int src = s < g.n_pairs ? s : 0;
     p.a_mn[s] = g.A[src].s_k != 1, p.b_mn[s] = g.B[src].s_k != 1;
     int rc = make_map(&maps[2 * s], g.A[src], g.M, g.K);
     if (rc) return rc;
-    rc = make_map(&maps[2 * s + 1], g.B[src], g.N, g.K);
+    rc = make_map(&maps[2 * s + 1], g.B[src], g.N, g.K, pair ? BN / 2 : BN);
     if (rc) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_BYTES));
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_BYTES));
     attr_set = true;
   }
-  const dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.split_k);
-  gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
-  HF_LAUNCH_CHECK();
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid.y, grid.x, grid.z), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = TcCfg<2>::SMEM_BYTES, cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, maps[0], maps[1], maps[2], maps[3], p);
+    if (le != cudaSuccess) {
+      int nclusters = -1;
+      cudaGetLastError();
+      cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, gemm_tc_kernel<2>, &cfg);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, gemm_tc_kernel<2>);
+      HF_REQUIRE(false, HF_ERR_CUDA, "pair launch failed: %s; grid (%u,%u,%u) smem %d; max active clusters %d (%s); regs %d static smem %zu maxdyn %d",
+                 cudaGetErrorString(le), grid.x, grid.y, grid.z, TcCfg<2>::SMEM_BYTES, nclusters, cudaGetErrorString(oe), fa.numRegs,
+                 fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+    }
+    note_launch();
+  } else {
+    gemm_tc_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    HF_LAUNCH_CHECK();
+  }
   return HF_OK;
 }
 

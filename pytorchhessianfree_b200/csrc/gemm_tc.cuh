@@ -8,4 +8,5 @@ constexpr int64_t kTcMinWork = 1 << 20;
 bool tc_supported(const GemmArgs& g);
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t stream);
 int set_tc_trace(void* d_buf);
+int set_tc_trace_iters(void* d_buf);
 }  // namespace hf

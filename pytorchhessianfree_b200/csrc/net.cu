@@ -975,6 +975,7 @@ int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t ac
 }
 
 int hf_debug_tc_trace(void* d_buf) { return set_tc_trace(d_buf); }
+int hf_debug_tc_trace_iters(void* d_buf) { return set_tc_trace_iters(d_buf); }
 
 int hf_contract(int32_t engine, int64_t M, int64_t N, int64_t K, int32_t n_pairs, const hf_operand* A,
                 const hf_operand* B, float* d_C, int64_t ldc, void* d_workspace, size_t workspace_bytes, void* stream) {
