@@ -117,6 +117,39 @@ def test_wide_layers_against_oracle(widths, loss, n, engine):
         close(prob.mvp(v.to(DEV)), want, curv)
 
 
+@pytest.mark.parametrize("loss,classes", [("ce", 10), ("mse", 3), ("bce", 32)])
+def test_fused_output_head_many_rows(loss, classes):
+    """The fused output head (csrc/head.cuh) with more rows than 32 x SM count, so that every CTA takes several
+    32-row steps and carries its head gradient across them; ragged widths and row count; against float64 autograd."""
+    n = 32 * 148 * 2 + 77
+    spec = dict(widths=[21, 70, classes], act="tanh", bias=[True, True], frozen=[], loss=loss)
+    loss_fn = build_loss(spec, "mean")
+    torch.manual_seed(3)
+    ref = build_model(spec)
+    x, t = make_data(spec, n, 5)
+    m64 = copy.deepcopy(ref).double()
+    p64 = list(m64.parameters())
+    out = m64(x.double())
+    l = loss_fn(out, t.double() if t.is_floating_point() else t)
+    v = torch.randn(sum(p.numel() for p in p64))
+    want = O.Gv(l, out, p64, v.double())
+    model = copy.deepcopy(ref).to(DEV)
+    dparams = list(model.parameters())
+    prog = lower_module(model, loss_fn, dparams)
+    theta = torch.cat([p.detach().reshape(-1) for p in dparams])
+    for engine in ("simt", "tc"):
+        net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine)
+        prob = NativeProblem(net, theta, "ggn", [(x.to(DEV), t.to(DEV))])
+        prob.linearize()
+        prob.gradient()
+        close(prob.mvp(v.to(DEV)), want, f"ggn ({engine})")
+        # two chunks (one of them a single ragged step) accumulate into the same vector
+        parts = NativeProblem(net, theta, "ggn", [(x[:5000].to(DEV), t[:5000].to(DEV)), (x[5000:].to(DEV), t[5000:].to(DEV))])
+        parts.linearize()
+        parts.gradient()
+        close(parts.mvp(v.to(DEV)), want, f"ggn chunked ({engine})")
+
+
 @pytest.mark.parametrize("engine", ["simt", "tc"])
 def test_linearity_and_symmetry_at_full_width(engine):
     """Size-independent properties at BASELINE configs[1] full size: B(av+bw) = aBv+bBw, v.Bw = w.Bv, v.Bv >= 0."""
