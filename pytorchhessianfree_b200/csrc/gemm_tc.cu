@@ -3,7 +3,7 @@
 //   C[M,N] = epilogue( sum_{s < n_pairs} A_s[M,K] * B_s[N,K]^T )        (same contract as gemm_simt.cuh)
 //
 // One CTA computes one 128x128 output tile (optionally one K-split of it):
-//   warp 4   TMA producer: cp.async.bulk.tensor 2-D boxes with SWIZZLE_128B into a 3-stage ring.  K-contiguous
+//   warp 4   TMA producer: cp.async.bulk.tensor 2-D boxes with SWIZZLE_128B into a 4-slot ring of raw FP32 tiles.  K-contiguous
 //            operands arrive as one [128 rows x 32 floats] box (K-major UMMA layout); MN-contiguous operands
 //            (transposed use: d^T a, d W) arrive as four [32 k-rows x 32 floats] boxes (MN-major UMMA layout), so no
 //            transposed copy of any activation or weight is ever made.  Out-of-bounds rows/columns are zero-filled
@@ -19,7 +19,9 @@
 //            rtol 1e-4 the path needs (~2^-13).  All-TF32 corrections (3xTF32) measured the same accuracy in the
 //            parity suite and 1.2x the main-loop time: the loop is bound by shared-memory bytes (TMA writes, splitter
 //            read/write, MMA operand reads), and the BF16 tiles halve the correction terms' operand bytes.
-//            tcgen05.commit releases the smem stage.
+//            tcgen05.commit releases the raw slot and the BF16 slot (a 2-slot ring of its own).
+//   pair     gemm_tc_kernel<2>: the same roles in a cluster of two CTAs along M with tcgen05.mma.cta_group::2 (M = 256),
+//            each CTA staging its A tile and half of B.  Parity-green, slower on B200, opt-in (HF_TC_PAIR=1).
 //   epilogue tcgen05.ld 32x32b -> registers -> the same fused epilogues as the SIMT engine (bias, act', act'', raw
 //            copy, split-K partials) -> global.
 #include <cuda.h>
