@@ -346,13 +346,19 @@ class HessianFree(torch.optim.Optimizer):
         dev = lambda dl: [(x.to(self.device), t.to(self.device)) for x, t in dl]  # noqa: E731
         grad_datalist = loss_datalist if grad_datalist is None else grad_datalist  # reference :575-579
         mvp_datalist = loss_datalist if mvp_datalist is None else mvp_datalist
-        problem = NativeProblem(
-            self._net_for(prog), theta, self._group["curvature_opt"],
-            mvp_data=dev(mvp_datalist),
-            grad_data=None if grad_datalist is mvp_datalist else dev(grad_datalist),
-            loss_data=None if loss_datalist is mvp_datalist else dev(loss_datalist),
-            group=self.process_group)
-        mvp_loss = problem.linearize()
+        net, mvp_data = self._net_for(prog), dev(mvp_datalist)
+        cached, self._prelinearized = getattr(self, "_prelinearized", None), None
+        same_lists = grad_datalist is mvp_datalist and loss_datalist is mvp_datalist
+        if (cached is not None and same_lists and self._group["curvature_opt"] == "ggn"
+                and cached[0] == self._problem_key(net, theta, mvp_data)):
+            _, problem, mvp_loss = cached  # linearised by get_preconditioner on the same data at the same parameters
+        else:
+            problem = NativeProblem(
+                net, theta, self._group["curvature_opt"], mvp_data=mvp_data,
+                grad_data=None if grad_datalist is mvp_datalist else dev(grad_datalist),
+                loss_data=None if loss_datalist is mvp_datalist else dev(loss_datalist),
+                group=self.process_group)
+            mvp_loss = problem.linearize()
         grad = problem.gradient()
         if loss_datalist is mvp_datalist:
             init_loss = float(mvp_loss.to(torch.float32).item())
@@ -415,8 +421,18 @@ class HessianFree(torch.optim.Optimizer):
         if prog.reduction != reduction:
             raise ValueError(f"the loss function reduces by {prog.reduction!r} but reduction={reduction!r} was given")
         theta = self._flat_params()
-        problem = NativeProblem(self._net_for(prog), theta, "ggn", [(inputs.to(self.device), targets.to(self.device))],
-                                group=self.process_group)
-        problem.linearize()
+        data = [(inputs.to(self.device), targets.to(self.device))]
+        net = self._net_for(prog)
+        problem = NativeProblem(net, theta, "ggn", data, group=self.process_group)
+        loss = problem.linearize()
         diag = problem.fisher_diag()
+        # The usual call order is get_preconditioner(x, t) followed by acc_step([(x, t)]) at the same parameters: keep
+        # the linearisation so that acc_step does not repeat the forward pass (dropped as soon as anything differs).
+        self._prelinearized = (self._problem_key(net, theta, data), problem, loss)
         return DiagonalPreconditioner(diag, self._group["damping"], 0.75 if exponent is None else exponent)
+
+    @staticmethod
+    def _problem_key(net, theta, data):
+        """Identity of a linearisation: net, parameter buffer and its version, data buffers and their versions."""
+        return (net.signature(), theta.data_ptr(), theta._version,
+                tuple((x.data_ptr(), x._version, tuple(x.shape), t.data_ptr(), t._version, tuple(t.shape)) for x, t in data))
