@@ -209,9 +209,22 @@ class HessianFree(torch.optim.Optimizer):
         step_vec = x_iters[-1]
         self._set_x0(self.cg_decay_x0 * x_iters[-1])  # the un-backtracked solution, Martens 2010 sec. 4.6
 
+        f_at_zero = None
         if problem is not None:
             params_vec = problem.theta
             tfunc = problem.target_function()
+            # one device pass and one host sync for everything the rest of the step usually asks: f(0) for the line
+            # search, f(x_0) and f(x_last) for the damping ratio, the first lookahead window of the backtracking walk
+            zero = torch.zeros_like(step_vec)
+            ask = [zero]
+            if self.adapt_damping:
+                ask += [x_iters[0], x_iters[-1]]
+            if self.use_cg_backtracking:
+                ask += [s for s in reversed(x_iters) if s is not None][:3]
+            if not self.use_linesearch:
+                ask = ask[1:]
+            primed = tfunc.prime(ask) if ask else []
+            f_at_zero = primed[0] if self.use_linesearch else None
         else:
             params_vec = parameters_to_vector(self._params_list).detach()
 
@@ -240,7 +253,8 @@ class HessianFree(torch.optim.Optimizer):
                 print(f"\nConstant lr = {lr:.6f}")
             final_loss = None
         else:
-            lr, final_loss = simple_linesearch(f=tfunc, f_grad_0=grad, step=step_vec, init_alpha=lr, verbose=self.verbose)
+            lr, final_loss = simple_linesearch(f=tfunc, f_grad_0=grad, step=step_vec, init_alpha=lr, verbose=self.verbose,
+                                               f_0=f_at_zero)
         state["learning_rates"].append(lr)
 
         if self.verbose:

@@ -127,9 +127,31 @@ class NativeProblem:
         return acc.to(torch.float32).tolist()
 
     def target_function(self):
-        """``tfunc`` of ``optimizer.py:290-294`` with a batched variant attached as ``.many``."""
-        def f(step):
-            return self.losses_at([step])[0]
+        """``tfunc`` of ``optimizer.py:290-294`` with a batched variant attached as ``.many``.
 
-        f.many = self.losses_at
+        Values are remembered per candidate tensor (address + version) for the life of the function object: damping
+        adaptation, backtracking and the line search ask for the same few candidates again (the last iterate three
+        times), and every question is a device pass plus a host synchronisation.  ``.prime(steps)`` evaluates a
+        list in one pass ahead of those questions."""
+        memo = {}  # key -> (tensor, value): holding the tensor keeps its address from being recycled under the key
+
+        def key(s):
+            return (s.data_ptr(), s._version, s.numel())
+
+        def many(steps):
+            missing = {}
+            for s in steps:
+                if key(s) not in memo:
+                    missing.setdefault(key(s), s)
+            if missing:
+                todo = list(missing.values())
+                for s, v in zip(todo, self.losses_at(todo)):
+                    memo[key(s)] = (s, v)
+            return [memo[key(s)][1] for s in steps]
+
+        def f(step):
+            return many([step])[0]
+
+        f.many = many
+        f.prime = many
         return f
