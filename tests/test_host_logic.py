@@ -100,3 +100,37 @@ def test_no_cpu_fallback():
     x, t = torch.rand(4, 3), torch.rand(4, 2)
     with pytest.raises(RuntimeError, match="no CPU path"):
         opt.step(lambda: (lambda o: (nn.functional.mse_loss(o, t), o))(model(x)))
+
+
+def test_target_function_memo_and_linesearch_shortcuts():
+    """The step asks for the same candidate losses several times; every distinct candidate is evaluated once, in as
+    few passes as possible, and the selection results equal the unmemoised ones (host logic only: a stub evaluates
+    the losses)."""
+    from pytorchhessianfree_b200.problem import NativeProblem
+
+    class Stub(NativeProblem):
+        def __init__(self):  # no device state: only target_function()/losses_at() are exercised
+            self.passes = []
+
+        def losses_at(self, steps):
+            self.passes.append(len(steps))
+            return [float((s - 1.0).pow(2).sum()) for s in steps]
+
+    stub = Stub()
+    f = stub.target_function()
+    cands = [torch.full((4,), v) for v in (0.0, 0.5, 0.9, 1.2, 2.0)]
+    zero = torch.zeros(4)
+    primed = f.prime([zero, cands[0], cands[-1], cands[-1], cands[-2], cands[-3]])
+    assert stub.passes == [5] and primed[2] == primed[3]  # duplicates share one evaluation
+    want_best = min(range(len(cands)), key=lambda i: float((cands[i] - 1.0).pow(2).sum()))
+    best, val = cg_efficient_backtracking(f, cands, lookahead=3)
+    assert best == want_best and val == pytest.approx(float((cands[best] - 1.0).pow(2).sum()))
+    assert stub.passes == [5, 1]  # the walk went one candidate beyond the primed window
+    grad = -torch.ones(4)
+    alpha, f_alpha = simple_linesearch(f, grad, cands[best], init_alpha=1.0, f_0=primed[0])
+    assert alpha == 1.0 and f_alpha == val and stub.passes == [5, 1]  # nothing new to evaluate
+    plain = lambda s: float((s - 1.0).pow(2).sum())  # noqa: E731
+    assert simple_linesearch(plain, grad, cands[best], init_alpha=1.0) == (alpha, f_alpha)
+    # a tensor modified in place is a new candidate
+    cands[0].add_(3.0)
+    assert f(cands[0]) == pytest.approx(4 * 4.0) and stub.passes[-1] == 1
