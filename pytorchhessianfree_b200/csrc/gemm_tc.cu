@@ -34,6 +34,9 @@ namespace hf {
 #ifndef HF_TC_ITER_TRACE
 #define HF_TC_ITER_TRACE 0  // compile with -DHF_TC_ITER_TRACE=1 for tools/tc_pipeline_trace.py (costs ~10 % of the loop)
 #endif
+#ifndef HF_TC_VARIANT
+#define HF_TC_VARIANT 0  // timing experiments only (wrong results): 1 = TMA only for the first ring fill, 2 = splitters
+#endif                   // idle, 4 = no MMAs; combine as a bit mask (tools/README.md)
 #ifndef HF_TC_RS1
 #define HF_TC_RS1 4
 #define HF_TC_LS1 2
@@ -514,6 +517,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int pr = it / n_kb, k0 = k_begin + (it % n_kb) * BKT;
         mbar_wait(&empty_raw[s], ph ^ 1);
         tc_mark_it(trace_it, 4, it);
+        if ((HF_TC_VARIANT & 1) && it >= RS) {
+          mbar_arrive(&full_raw[s]);
+          continue;
+        }
         mbar_expect_tx(&full_raw[s], TILE_BYTES + Cfg::B_BYTES);
         uint8_t* rawA = tiles + s * Cfg::RAW_BYTES;
         uint8_t* rawB = rawA + Cfg::OFF_RAW_B;
@@ -560,10 +567,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t loB = loA + Cfg::OFF_B16, hiB = loB + Cfg::B_BYTES / 2;
         if (NCTA == 1) {
 #pragma unroll
-          for (int ks = 0; ks < BKT / 8; ++ks)
+          for (int ks = 0; ks < ((HF_TC_VARIANT & 4) ? 0 : BKT / 8); ++ks)
             umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], ks), operand_desc(rawB, p.b_mn[pr], ks), idesc, (it | ks) != 0);
 #pragma unroll
-          for (int ks = 0; ks < BKT / 16; ++ks) {
+          for (int ks = 0; ks < ((HF_TC_VARIANT & 4) ? 0 : BKT / 16); ++ks) {
             umma_bf16(tmem_base, corr_desc(loA, p.a_mn[pr], ks), corr_desc(hiB, p.b_mn[pr], ks), idesc16, 1);
             umma_bf16(tmem_base, corr_desc(hiA, p.a_mn[pr], ks), corr_desc(loB, p.b_mn[pr], ks), idesc16, 1);
           }
@@ -597,12 +604,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (it == 0) tc_mark(2, threadIdx.x == 0, p.trace_epoch);
       if (threadIdx.x == 0) tc_mark_it(trace_it, 1, it);
       const uint32_t st = smem_u32(tiles + s * Cfg::RAW_BYTES), lo = smem_u32(lo_tiles + l * Cfg::LO_BYTES);
+      if (!(HF_TC_VARIANT & 2)) {
       if (p.a_mn[sp_pr]) split_tile<true, BM>(st, lo, lo + TILE_BYTES / 2);
       else split_tile<false, BM>(st, lo, lo + TILE_BYTES / 2);
       if (p.b_mn[sp_pr])
         split_tile<true, Cfg::B_ROWS>(st + Cfg::OFF_RAW_B, lo + Cfg::OFF_B16, lo + Cfg::OFF_B16 + Cfg::B_BYTES / 2);
       else
         split_tile<false, Cfg::B_ROWS>(st + Cfg::OFF_RAW_B, lo + Cfg::OFF_B16, lo + Cfg::OFF_B16 + Cfg::B_BYTES / 2);
+      }
       if (++sp_kb == n_kb) sp_kb = 0, ++sp_pr;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA unit
       __syncwarp();
