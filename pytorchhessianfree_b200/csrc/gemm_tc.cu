@@ -20,7 +20,11 @@
 //            parity suite and 1.2x the main-loop time: the loop is bound by shared-memory bytes (TMA writes, splitter
 //            read/write, MMA operand reads), and the BF16 tiles halve the correction terms' operand bytes.
 //            tcgen05.commit releases the raw slot and the BF16 slot (a 2-slot ring of its own).
-//   pair     gemm_tc_kernel<2>: the same roles in a cluster of two CTAs along M with tcgen05.mma.cta_group::2 (M = 256),
+//   TS       gemm_tc_kernel<1, true> (HF_TC_TS=1): the splitters put the A operand (TF32 words, BF16 lo/hi pairs) into
+//            TMEM with tcgen05.st and the MMAs run in TS mode, so the instruction fetches only B from shared memory.
+//            Parity-green on the contraction suite; same speed for K-major A, 7-10 % faster when A is MN-major
+//            (weight-gradient shapes).  Opt-in until it has been through the whole parity suite.
+//   pair     gemm_tc_kernel<2, false>: the same roles in a cluster of two CTAs along M with tcgen05.mma.cta_group::2 (M = 256),
 //            each CTA staging its A tile and half of B.  Parity-green, slower on B200, opt-in (HF_TC_PAIR=1).
 //   epilogue tcgen05.ld 32x32b -> registers -> the same fused epilogues as the SIMT engine (bias, act', act'', raw
 //            copy, split-K partials) -> global.
@@ -37,6 +41,9 @@ namespace hf {
 #ifndef HF_TC_VARIANT
 #define HF_TC_VARIANT 0  // timing experiments only (wrong results): 1 = TMA only for the first ring fill, 2 = splitters
 #endif                   // idle, 4 = no MMAs; combine as a bit mask (tools/README.md)
+#ifndef HF_TC_DUAL_ACC
+#define HF_TC_DUAL_ACC 0  // 1: TF32 main term and BF16 corrections accumulate in two TMEM tiles (two independent MMA
+#endif                    // chains).  Parity-green, no change in speed on B200 (0.66 us per k-block), so off.
 #ifndef HF_TC_RS1
 #define HF_TC_RS1 4
 #define HF_TC_LS1 2
@@ -156,6 +163,70 @@ __device__ __forceinline__ float tf32_round(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// ---- A operand from TMEM (TS mode): the instruction fetches only B from shared memory ----
+__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one 32-bit word per lane and column: lane = this thread's row, 16 consecutive columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+constexpr int kTsAcols = 64;  // TMEM columns of one A slot: 32 TF32 words | 16 packed lo16 | 16 packed hi16
+
+// Row `m` (= threadIdx.x = TMEM lane) of the raw FP32 A tile -> TMEM: x_t words, bf16(x - x_t) and bf16(x) packed in pairs.
+template <bool MN>
+__device__ __forceinline__ void split_row_to_tmem(uint32_t src, uint32_t taddr, int m) {
+  float x[BKT];
+  if (!MN) {  // [128 rows][8 x 16 B], chunk ^= row & 7
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(x[4 * j]), "=f"(x[4 * j + 1]), "=f"(x[4 * j + 2]), "=f"(x[4 * j + 3])
+                   : "r"(src + m * 128 + ((j ^ (m & 7)) << 4)));
+  } else {    // column blocks of 32 rows: [32 k-rows][4 x 32 B], 32-byte chunk ^= k-row & 3
+    const uint32_t base = src + (m >> 5) * 4096 + ((m & 7) << 2);
+    const int c = (m & 31) >> 3;
+#pragma unroll
+    for (int k = 0; k < BKT; ++k)
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[k]) : "r"(base + k * 128 + ((c ^ (k & 3)) << 5)));
+  }
+  uint32_t w[16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // TF32 operand: the raw words (the MMA unit truncates)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(x[16 * h + i]);
+    tmem_st16(taddr + 16 * h, w);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float l0 = x[2 * i] - __uint_as_float(__float_as_uint(x[2 * i]) & 0xffffe000u);
+    const float l1 = x[2 * i + 1] - __uint_as_float(__float_as_uint(x[2 * i + 1]) & 0xffffe000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(l1), "f"(l0));
+  }
+  tmem_st16(taddr + 32, w);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(x[2 * i + 1]), "f"(x[2 * i]));
+  tmem_st16(taddr + 48, w);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ---- CTA-pair (cta_group::2) variants ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -448,12 +519,16 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, uint32_t st
   }
 }
 
-template <int NCTA>
+template <int NCTA, bool TS>
 __global__ void __launch_bounds__(TC_THREADS, NCTA == 1 ? kCtasPerSm : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ TcArgs p) {
   using Cfg = TcCfg<NCTA>;
   constexpr int RS = Cfg::RAW_STAGES, LS = Cfg::LO_STAGES;
+  static_assert(!(TS && NCTA == 2), "the TMEM-operand variant is single-CTA");
+  // columns: accumulator [0,128) (+ second accumulator [128,256) for the correction terms) (+ TS: LS slots of A)
+  constexpr int ACC2 = (HF_TC_DUAL_ACC && !TS && NCTA == 1) ? BN : 0;
+  constexpr int TMEM_COLS = TS ? 256 : BN + ACC2;
   const GemmArgs& g = p.g;
   if (g.skip && *g.skip) return;  // uniform (also across a CTA pair): solver already terminated
   // pair: rank 0 (even tile row) is the leader and issues the M = 256 MMAs for both CTAs
@@ -495,7 +570,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (warp == 5) {
     if (NCTA == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     } else {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
@@ -565,7 +640,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t idesc = idesc_of(pr, 2u), idesc16 = idesc_of(pr, 1u);
         const uint32_t loA = smem_u32(lo_tiles + l * Cfg::LO_BYTES), hiA = loA + TILE_BYTES / 2;
         const uint32_t loB = loA + Cfg::OFF_B16, hiB = loB + Cfg::B_BYTES / 2;
-        if (NCTA == 1) {
+        if (TS) {
+          // A from TMEM: always "K-major" (lane = row, columns = K), whatever the layout of A in global memory
+          const uint32_t clr = ~(1u << 15);
+          const uint32_t a_t = tmem_base + BN + l * kTsAcols;
+#pragma unroll
+          for (int ks = 0; ks < BKT / 8; ++ks)
+            umma_ts_tf32(tmem_base, a_t + 8 * ks, operand_desc(rawB, p.b_mn[pr], ks), idesc & clr, (it | ks) != 0);
+#pragma unroll
+          for (int ks = 0; ks < BKT / 16; ++ks) {
+            umma_ts_bf16(tmem_base, a_t + 32 + 8 * ks, corr_desc(hiB, p.b_mn[pr], ks), idesc16 & clr, 1);
+            umma_ts_bf16(tmem_base, a_t + 48 + 8 * ks, corr_desc(loB, p.b_mn[pr], ks), idesc16 & clr, 1);
+          }
+          umma_commit(&empty_raw[s]);
+          umma_commit(&empty_lo[l]);
+        } else if (NCTA == 1 && ACC2) {
+          // two independent accumulation chains, interleaved: the MMA pipe does not have to wait for the previous
+          // read-modify-write of the same TMEM tile before it starts the next instruction
+          const uint32_t d2 = tmem_base + ACC2;
+#pragma unroll
+          for (int ks = 0; ks < BKT / 16; ++ks) {
+            umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], 2 * ks), operand_desc(rawB, p.b_mn[pr], 2 * ks), idesc, (it | ks) != 0);
+            umma_bf16(d2, corr_desc(loA, p.a_mn[pr], ks), corr_desc(hiB, p.b_mn[pr], ks), idesc16, (it | ks) != 0);
+            umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], 2 * ks + 1), operand_desc(rawB, p.b_mn[pr], 2 * ks + 1), idesc, 1);
+            umma_bf16(d2, corr_desc(hiA, p.a_mn[pr], ks), corr_desc(loB, p.b_mn[pr], ks), idesc16, 1);
+          }
+          umma_commit(&empty_raw[s]);
+          umma_commit(&empty_lo[l]);
+        } else if (NCTA == 1) {
 #pragma unroll
           for (int ks = 0; ks < ((HF_TC_VARIANT & 4) ? 0 : BKT / 8); ++ks)
             umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], ks), operand_desc(rawB, p.b_mn[pr], ks), idesc, (it | ks) != 0);
@@ -605,7 +707,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (threadIdx.x == 0) tc_mark_it(trace_it, 1, it);
       const uint32_t st = smem_u32(tiles + s * Cfg::RAW_BYTES), lo = smem_u32(lo_tiles + l * Cfg::LO_BYTES);
       if (!(HF_TC_VARIANT & 2)) {
-      if (p.a_mn[sp_pr]) split_tile<true, BM>(st, lo, lo + TILE_BYTES / 2);
+      if (TS) {
+        const uint32_t a_t = tmem_base + ((uint32_t)(warp * 32) << 16) + BN + l * kTsAcols;
+        if (p.a_mn[sp_pr]) split_row_to_tmem<true>(st, a_t, threadIdx.x);
+        else split_row_to_tmem<false>(st, a_t, threadIdx.x);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      } else if (p.a_mn[sp_pr]) split_tile<true, BM>(st, lo, lo + TILE_BYTES / 2);
       else split_tile<false, BM>(st, lo, lo + TILE_BYTES / 2);
       if (p.b_mn[sp_pr])
         split_tile<true, Cfg::B_ROWS>(st + Cfg::OFF_RAW_B, lo + Cfg::OFF_B16, lo + Cfg::OFF_B16 + Cfg::B_BYTES / 2);
@@ -636,6 +743,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       float v[16];
       if (total > 0) {
         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
+        if (ACC2) {
+          float v2[16];
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + ACC2 + c, v2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += v2[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -670,7 +783,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_mark(4, threadIdx.x == 0, p.trace_epoch);
   if (warp == 5) {
     if (NCTA == 1)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     else
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
   }
@@ -771,8 +884,9 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_BYTES));
-    HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_BYTES));
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_BYTES));
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_BYTES));
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_BYTES));
     attr_set = true;
   }
   if (pair) {
@@ -782,20 +896,23 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t stream) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, maps[0], maps[1], maps[2], maps[3], p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, false>, maps[0], maps[1], maps[2], maps[3], p);
     if (le != cudaSuccess) {
       int nclusters = -1;
       cudaGetLastError();
-      cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, gemm_tc_kernel<2>, &cfg);
+      cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, gemm_tc_kernel<2, false>, &cfg);
       cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, gemm_tc_kernel<2>);
+      cudaFuncGetAttributes(&fa, gemm_tc_kernel<2, false>);
       HF_REQUIRE(false, HF_ERR_CUDA, "pair launch failed: %s; grid (%u,%u,%u) smem %d; max active clusters %d (%s); regs %d static smem %zu maxdyn %d",
                  cudaGetErrorString(le), grid.x, grid.y, grid.z, TcCfg<2>::SMEM_BYTES, nclusters, cudaGetErrorString(oe), fa.numRegs,
                  fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
     }
     note_launch();
   } else {
-    gemm_tc_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    // HF_TC_TS=1: A operand through TMEM (experimental)
+    static const bool ts = getenv("HF_TC_TS") && atoi(getenv("HF_TC_TS")) != 0;
+    if (ts) gemm_tc_kernel<1, true><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    else gemm_tc_kernel<1, false><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
     HF_LAUNCH_CHECK();
   }
   return HF_OK;
