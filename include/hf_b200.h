@@ -74,7 +74,9 @@ long long hf_debug_launch_count(void);
  * per CTA: [cta][0] start, [1] partial p.Ap ready, [2] alpha known, [3] x/r updated, [4] beta known, [5] p written */
 int hf_debug_pcg_trace(void* d_buf);
 /* same for the tcgen05 contraction kernel: [cta][0] entry, [1] prologue done (barriers, TMEM), [2] first stage landed,
- * [3] accumulator complete, [4] epilogue done (d_buf >= 8 * n_ctas uint64) */
+ * [3] accumulator complete, [4] epilogue done, [5] TMEM -> shared done.  Consecutive launches after the call write
+ * consecutive blocks of 1024 CTA records (d_buf >= launches * 1024 * 8 uint64), so gaps between kernels can be read
+ * off too; NULL switches the trace off. */
 int hf_debug_tc_trace(void* d_buf);
 /* per-k-block pipeline trace of CTA (0,0,0) of the same kernel, first 64 k-blocks: [it][0] TMA issued, [1] raw tiles seen
  * by the splitters, [2] split done, [3] MMAs issued, [4] producer's slot wait done (d_buf >= 64 * 8 uint64) */
