@@ -219,7 +219,10 @@ const float* hf_lin_logits(const hf_lin_t* lin);
 /* ------------------------------------------------------------------------------------------
  * Stand-alone contraction used by the kernels above, exported for unit tests and profiling:
  * C[M,N] = sum_s A_s[M,K] * B_s[N,K]^T  (n_pairs in {1,2}), element strides given per operand.
- * engine: 0 = FP32 SIMT tiles, 1 = tcgen05 split-precision tiles (requires the alignment it reports).
+ * engine: 0 = FP32 SIMT tiles, 1 = tcgen05 split-precision 128x128 tiles (requires the alignment it reports),
+ * 2 = tcgen05 256x256 CTA-pair tiles on pre-split operand images; engine 2 builds the images of its operands in
+ * d_workspace first (at least hf_contract_workspace_bytes bytes, 256-byte aligned); 3 = engine 2 with the images left in
+ * the workspace by a previous engine-2 call with the same arguments (times the tile kernel alone).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const float* d_ptr;
@@ -227,6 +230,7 @@ typedef struct {
   int64_t stride_k;  /* element stride along K; one of the two strides must be 1 */
 } hf_operand;
 
+size_t hf_contract_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t n_pairs);
 int hf_contract(int32_t engine, int64_t M, int64_t N, int64_t K, int32_t n_pairs, const hf_operand* A,
                 const hf_operand* B, float* d_C, int64_t ldc, void* d_workspace, size_t workspace_bytes, void* stream);
 

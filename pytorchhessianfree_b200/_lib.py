@@ -83,6 +83,7 @@ SIGNATURES = {
     "hf_matvec_phase": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "hf_net_first_layer_span": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "hf_lin_logits": (_vp, [_vp]),
+    "hf_contract_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "hf_contract": (C.c_int, [_i32, _i64, _i64, _i64, _i32, C.POINTER(Operand), C.POINTER(Operand), _vp, _i64, _vp, _sz,
                               _vp]),
 }
@@ -96,17 +97,18 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("HF_B200_LIB", LIB_PATH)  # override: A/B builds of the same ABI
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: the sm_100a kernels are not built. Run "
+            f"{path} is missing: the sm_100a kernels are not built. Run "
             "`python -m pytorchhessianfree_b200.build` (there is no CPU or PyTorch fallback)."
         )
-    lib = C.CDLL(os.environ.get("HF_B200_LIB", LIB_PATH))  # override: A/B builds of the same ABI
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
     if lib.hf_abi_version() != 1:
-        raise RuntimeError(f"{LIB_PATH}: ABI version {lib.hf_abi_version()} != 1; rebuild")
+        raise RuntimeError(f"{path}: ABI version {lib.hf_abi_version()} != 1; rebuild")
     _lib = lib
     return lib
 

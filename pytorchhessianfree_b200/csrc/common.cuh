@@ -35,6 +35,16 @@ void note_launch();
     }                                \
   } while (0)
 
+// cudaFuncSetAttribute opt-ins (large dynamic shared memory) are per device: `seen` is a static table owned by the call
+// site; true the first time that site runs on the current device (a process may drive several GPUs).
+inline bool first_use_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 constexpr int kMaxCtas = 256;  // upper bound on the persistent grid (148 SMs on B200)
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {

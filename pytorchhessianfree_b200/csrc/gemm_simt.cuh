@@ -23,10 +23,23 @@ enum Epilogue {
   EPI_DACT_H = 4      // C = acc * act'(aux) + ga * act''(aux) * rz (Hessian backward data)
 };
 
+// Split-precision image of an FP32 matrix: two BF16 planes with the matrix's own orientation and a row pitch of
+// their own (a multiple of 8 elements = 16 B, what TMA needs): hi = bf16(x), lo = bf16(x - tf32_trunc(x)).
+// Together with the FP32 words themselves (kind::tf32 reads their top 19 bits) these are the three operand forms of
+// the split-precision product  A B ~= A_t B_t + A_lo B_hi + A_hi B_lo.  The pre-split tensor engine (gemm_tc2.cu)
+// loads them ready-made; they are written once per linearisation for operands that are constant during a solve
+// (inputs, activations, weights) and by the producing kernel's epilogue for the per-iteration ones.
+struct Image16 {
+  uint16_t* hi;     // plane 0; nullptr = no image
+  int64_t plane;    // element offset from the hi plane to the lo plane
+  int64_t ld;       // row pitch in elements (multiple of 8)
+};
+
 struct Operand {
   const float* ptr;
   int64_t s_mn;
   int64_t s_k;
+  Image16 img;  // optional (zero-initialised by the brace initialisers used everywhere)
 };
 
 struct GemmArgs {
@@ -47,6 +60,7 @@ struct GemmArgs {
   int k_per_split;  // multiple of BK
   const int32_t* skip;
   float* colpart;  // tensor-core engine only: colpart[blockIdx.y * N + n] = column sums of the stored tile rows
+  Image16 c_img;   // optional: the tensor engines also store the split-precision image of C (row pitch c_img.ld)
 };
 
 __device__ __forceinline__ float act_apply(int act, float z) {

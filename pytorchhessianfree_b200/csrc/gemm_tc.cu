@@ -28,34 +28,25 @@
 //            each CTA staging its A tile and half of B.  Parity-green, slower on B200, opt-in (HF_TC_PAIR=1).
 //   epilogue tcgen05.ld 32x32b -> registers -> the same fused epilogues as the SIMT engine (bias, act', act'', raw
 //            copy, split-K partials) -> global.
-#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
-#include "gemm_tc.cuh"
+#include <unordered_map>
+
+#include "tc_common.cuh"
 
 namespace hf {
 
 #ifndef HF_TC_ITER_TRACE
 #define HF_TC_ITER_TRACE 0  // compile with -DHF_TC_ITER_TRACE=1 for tools/tc_pipeline_trace.py (costs ~10 % of the loop)
 #endif
-#ifndef HF_TC_VARIANT
-#define HF_TC_VARIANT 0  // timing experiments only (wrong results): 1 = TMA only for the first ring fill, 2 = splitters
-#endif                   // idle, 4 = no MMAs; combine as a bit mask (tools/README.md)
-#ifndef HF_TC_DUAL_ACC
-#define HF_TC_DUAL_ACC 0  // 1: TF32 main term and BF16 corrections accumulate in two TMEM tiles (two independent MMA
-#endif                    // chains).  Parity-green, no change in speed on B200 (0.66 us per k-block), so off.
 #ifndef HF_TC_RS1
 #define HF_TC_RS1 4
 #define HF_TC_LS1 2
 #endif
 
-// Tile 128x128, k-block of BKT floats.  BKT = 32: 128-byte swizzle rows, 193 KB of shared memory, one CTA per SM.
-// BKT = 16 (64-byte rows, 97 KB, two CTAs per SM) is supported by every piece below and was measured: the co-resident
-// CTAs overlap each other's prologue/epilogue, but the main loop pays one mbarrier round trip per 16 instead of 32
-// columns (1.15 vs 0.73 us per 32 columns) and the product got 10 % slower, so 32 it is.
-constexpr int BM = 128, BN = 128, BKT = 32;
-constexpr int kCtasPerSm = BKT == 32 ? 1 : 2;
-constexpr uint32_t kKMajorLayout = BKT == 32 ? 2u : 4u;  // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+// Tile 128x128, k-block of BKT = 32 floats (128-byte swizzle rows), 193 KB of shared memory, one CTA per SM.
+constexpr int BM = 128, BN = 128;
 constexpr int TILE_BYTES = BM * BKT * 4;                  // 16 KB per 128-row FP32 operand tile
 constexpr int TC_THREADS = 192;
 // NCTA = 1: one CTA per tile.  NCTA = 2: a CTA pair (cluster of two along M, tcgen05 cta_group::2) computes two
@@ -111,83 +102,6 @@ struct TcArgs {
   int trace_epoch;       // block of the trace buffer this launch writes (0 unless tracing)
 };
 
-// ---- PTX wrappers ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// round to the nearest TF32 value (the MMA unit would otherwise truncate the low word: a bias of ~2^-22 per operand)
-__device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-// ---- A operand from TMEM (TS mode): the instruction fetches only B from shared memory ----
-__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// one 32-bit word per lane and column: lane = this thread's row, 16 consecutive columns
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 constexpr int kTsAcols = 64;  // TMEM columns of one A slot: 32 TF32 words | 16 packed lo16 | 16 packed hi16
 
 // Row `m` (= threadIdx.x = TMEM lane) of the raw FP32 A tile -> TMEM: x_t words, bf16(x - x_t) and bf16(x) packed in pairs.
@@ -227,99 +141,6 @@ __device__ __forceinline__ void split_row_to_tmem(uint32_t src, uint32_t taddr, 
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// ---- CTA-pair (cta_group::2) variants ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// completion of all prior MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46)
-// version[46,48)=1 layout_type[61,64)=2); all offsets in 16-byte units.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-// operand tile of 128 (M or N) x 32 (K) floats at `base`, k-step ks (8 floats):
-//   K-major : rows of BKT*4 bytes (SWIZZLE_128B, type 2, for BKT = 32; SWIZZLE_64B, type 4, for BKT = 16), 8-row
-//             swizzle atoms 8*BKT*4 bytes apart (SBO); step = +32 B in the row
-//   MN-major: 32-bit operands only exist in SWIZZLE_128B_BASE32B (type 1; cute Layout_MN_SW128_32B_Atom, TMA
-//             SWIZZLE_128B_ATOM_32B): atoms of [4 k-rows x 128 B] 512 B apart along K (SBO); 4 column blocks of
-//             [32 k-rows x 128 B] 4096 B apart along MN (LBO); one k-step = 8 k-rows = +1024 B
-__device__ __forceinline__ uint64_t operand_desc(uint32_t base, int mn_major, int ks) {
-  return mn_major ? smem_desc(base + ks * 1024, BKT * 128, 512, 1) : smem_desc(base + ks * 32, 16, 8 * BKT * 4, kKMajorLayout);
-}
-
-// BF16 correction tile of 128 (M or N) x 32 (K) bf16 at `base`, k-step ks (16 bf16):
-//   K-major : 64-byte rows, SWIZZLE_64B (type 4), 8-row atoms 512 B apart (SBO); step = +32 B in the row
-//   MN-major: two column blocks of [32 k-rows x 128 B = 64 bf16] 4096 B apart along MN (LBO), SWIZZLE_128B (type 2),
-//             atoms of 8 k-rows 1024 B apart along K (SBO); one k-step = 16 k-rows = +2048 B
-__device__ __forceinline__ uint64_t corr_desc(uint32_t base, int mn_major, int ks) {
-  return mn_major ? smem_desc(base + ks * 2048, 4096, 1024, 2) : smem_desc(base + ks * 32, 16, 512, 4);
-}
 
 // Splitter: one FP32 operand tile (in its UMMA/TMA swizzled layout) -> two BF16 tiles of the same major-ness:
 // hi16 = bf16(x) and lo16 = bf16(x - trunc_tf32(x)).  The FP32 tile is element (row, k-quad) addressed by undoing the
@@ -360,175 +181,16 @@ __device__ __forceinline__ void split_tile(uint32_t src, uint32_t lo16, uint32_t
   }
 }
 
-// ---- fused epilogue, one specialisation per (epilogue kind, activation): the row loop is straight-line vector code
-// (with one warp per scheduler every branch and dependent ALU op is exposed latency, so nothing is decided per element)
-template <int ACT>
-__device__ __forceinline__ float d1(float s) {
-  if (ACT == HF_ACT_RELU) return s > 0.f ? 1.f : 0.f;
-  if (ACT == HF_ACT_SIGMOID) return s * (1.f - s);
-  if (ACT == HF_ACT_TANH) return 1.f - s * s;
-  return 1.f;
-}
-template <int ACT>
-__device__ __forceinline__ float d2(float s) {
-  if (ACT == HF_ACT_SIGMOID) return s * (1.f - s) * (1.f - 2.f * s);
-  if (ACT == HF_ACT_TANH) return -2.f * s * (1.f - s * s);
-  return 0.f;
-}
-template <int ACT>
-__device__ __forceinline__ float act_fwd(float z) {
-  if (ACT == HF_ACT_RELU) return z > 0.f ? z : 0.f;
-  if (ACT == HF_ACT_SIGMOID) return 1.f / (1.f + expf(-z));
-  if (ACT == HF_ACT_TANH) return tanhf(z);
-  return z;
-}
-
-template <bool VEC>
-__device__ __forceinline__ void ld4(const float* p, int cnt, float (&o)[4]) {
-  if (VEC) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    o[0] = t.x, o[1] = t.y, o[2] = t.z, o[3] = t.w;
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = e < cnt ? p[e] : 0.f;
-  }
-}
-template <bool VEC>
-__device__ __forceinline__ void st4(float* p, int cnt, const float (&o)[4]) {
-  if (VEC) {
-    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (e < cnt) p[e] = o[e];
-  }
-}
-
-// rows [m_base, m_base+32) x columns [n, n+4) of the tile; `stage` holds the warp's 32 accumulator rows
-template <int EPI, int ACT, bool VEC>
-__device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t stage, int m_base, int n, int lane, int cnt,
-                                              float (&cs)[4]) {
-  constexpr int LDS_ROW = BN + 4;
-  constexpr bool NEED_AUX = ACT != HF_ACT_NONE && EPI >= EPI_BIAS_DACT;
-  // Every field is copied into a register first: `g` lives in the kernel-parameter window and is read through a
-  // generic pointer, which the compiler must otherwise re-load after every global store (possible aliasing).
-  const int64_t ldc = g.ldc, ldaux = g.ldaux;
-  float* const C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0) + n;
-  float* const C2 = g.C2 ? g.C2 + n : nullptr;
-  const float* const aux = g.aux ? g.aux + n : nullptr;
-  const float* const hga = g.h_ga ? g.h_ga + n : nullptr;
-  const float* const hrz = g.h_rz ? g.h_rz + n : nullptr;
-  const float alpha = g.alpha;
-  const int rows = min(32, g.M - m_base);
-  float bi[4] = {0.f, 0.f, 0.f, 0.f};
-  if ((EPI == EPI_STORE || EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_DACT) && g.bias) ld4<VEC>(g.bias + n, cnt, bi);
-  constexpr int RB = 4;  // rows in flight: their global loads are all issued before the first use
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // column sums in registers (`cs` is memory: it crosses a call boundary)
-#pragma unroll 1
-  for (int r0 = 0; r0 < rows; r0 += RB) {
-    float x[RB][4], au[RB][4], ga[RB][4], rz[RB][4];
-#pragma unroll
-    for (int j = 0; j < RB; ++j) {
-      const int r = min(r0 + j, rows - 1);  // clamp: tail slots re-read the last row and are not stored
-      const int64_t m = m_base + r;
-      float4 t;  // explicit shared-space load (the pointer's address space is not visible to the compiler here)
-      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(stage + (r * LDS_ROW + lane * 4) * 4));
-      x[j][0] = t.x, x[j][1] = t.y, x[j][2] = t.z, x[j][3] = t.w;
-      if (NEED_AUX) ld4<VEC>(aux + m * ldaux, cnt, au[j]);
-      if (EPI == EPI_DACT_H && hga) {
-        ld4<VEC>(hga + m * ldaux, cnt, ga[j]);
-        ld4<VEC>(hrz + m * ldaux, cnt, rz[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < RB; ++j) {
-      if (r0 + j >= rows) break;
-      const int64_t m = m_base + r0 + j;
-      if (EPI == EPI_STORE) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) x[j][e] = alpha * x[j][e] + bi[e];
-      } else if (EPI == EPI_BIAS_ACT) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) x[j][e] = act_fwd<ACT>(x[j][e] + bi[e]);
-      } else if (EPI == EPI_BIAS_DACT) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) x[j][e] += bi[e];
-        if (C2) st4<VEC>(C2 + m * ldc, cnt, x[j]);
-        if (NEED_AUX)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[j][e] *= d1<ACT>(au[j][e]);
-      } else if (EPI == EPI_DACT) {
-        if (C2) st4<VEC>(C2 + m * ldc, cnt, x[j]);
-        if (NEED_AUX)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[j][e] *= d1<ACT>(au[j][e]);
-      } else {  // EPI_DACT_H
-        if (NEED_AUX) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[j][e] *= d1<ACT>(au[j][e]);
-          if (hga)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[j][e] += ga[j][e] * d2<ACT>(au[j][e]) * rz[j][e];
-        }
-      }
-      st4<VEC>(C + m * ldc, cnt, x[j]);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[e] += x[j][e];
-    }
-    if (r0 == 0) tc_mark(6, threadIdx.x == 0);
-  }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) cs[e] = acc[e];
-  tc_mark(7, threadIdx.x == 0);
-}
-
-template <int EPI, int ACT>
-__device__ __forceinline__ void epilogue_vec(const GemmArgs& g, uint32_t stage, int m_base, int n, int lane,
-                                             float (&cs)[4]) {
-  const int cnt = min(4, g.N - n);
-  if (cnt <= 0 || m_base >= g.M) return;
-  float* C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0);
-  const bool al16 = ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(g.C2) | reinterpret_cast<uintptr_t>(g.aux) |
-                      reinterpret_cast<uintptr_t>(g.h_ga) | reinterpret_cast<uintptr_t>(g.h_rz) |
-                      reinterpret_cast<uintptr_t>(g.bias)) & 15u) == 0 && g.ldc % 4 == 0 && g.ldaux % 4 == 0;
-  if (al16 && cnt == 4)
-    epilogue_rows<EPI, ACT, true>(g, stage, m_base, n, lane, cnt, cs);
-  else
-    epilogue_rows<EPI, ACT, false>(g, stage, m_base, n, lane, cnt, cs);
-}
-
-template <int EPI>
-__device__ __forceinline__ void epilogue_act(const GemmArgs& g, uint32_t stage, int m_base, int n, int lane,
-                                             float (&cs)[4]) {
-  switch (g.act) {
-    case HF_ACT_RELU: epilogue_vec<EPI, HF_ACT_RELU>(g, stage, m_base, n, lane, cs); break;
-    case HF_ACT_SIGMOID: epilogue_vec<EPI, HF_ACT_SIGMOID>(g, stage, m_base, n, lane, cs); break;
-    case HF_ACT_TANH: epilogue_vec<EPI, HF_ACT_TANH>(g, stage, m_base, n, lane, cs); break;
-    default: epilogue_vec<EPI, HF_ACT_NONE>(g, stage, m_base, n, lane, cs); break;
-  }
-}
-
-__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, uint32_t stage, int m_base, int n, int lane,
-                                               float (&cs)[4]) {
-  switch (g.epi) {
-    case EPI_STORE: epilogue_vec<EPI_STORE, HF_ACT_NONE>(g, stage, m_base, n, lane, cs); break;
-    case EPI_BIAS_ACT: epilogue_act<EPI_BIAS_ACT>(g, stage, m_base, n, lane, cs); break;
-    case EPI_BIAS_DACT: epilogue_act<EPI_BIAS_DACT>(g, stage, m_base, n, lane, cs); break;
-    case EPI_DACT: epilogue_act<EPI_DACT>(g, stage, m_base, n, lane, cs); break;
-    default: epilogue_act<EPI_DACT_H>(g, stage, m_base, n, lane, cs); break;
-  }
-}
 
 template <int NCTA, bool TS>
-__global__ void __launch_bounds__(TC_THREADS, NCTA == 1 ? kCtasPerSm : 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ TcArgs p) {
   using Cfg = TcCfg<NCTA>;
   constexpr int RS = Cfg::RAW_STAGES, LS = Cfg::LO_STAGES;
   static_assert(!(TS && NCTA == 2), "the TMEM-operand variant is single-CTA");
-  // columns: accumulator [0,128) (+ second accumulator [128,256) for the correction terms) (+ TS: LS slots of A)
-  constexpr int ACC2 = (HF_TC_DUAL_ACC && !TS && NCTA == 1) ? BN : 0;
-  constexpr int TMEM_COLS = TS ? 256 : BN + ACC2;
+  // columns: accumulator [0,128) (+ TS: LS slots of A)
+  constexpr int TMEM_COLS = TS ? 256 : BN;
   const GemmArgs& g = p.g;
   if (g.skip && *g.skip) return;  // uniform (also across a CTA pair): solver already terminated
   // pair: rank 0 (even tile row) is the leader and issues the M = 256 MMAs for both CTAs
@@ -592,10 +254,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int pr = it / n_kb, k0 = k_begin + (it % n_kb) * BKT;
         mbar_wait(&empty_raw[s], ph ^ 1);
         tc_mark_it(trace_it, 4, it);
-        if ((HF_TC_VARIANT & 1) && it >= RS) {
-          mbar_arrive(&full_raw[s]);
-          continue;
-        }
         mbar_expect_tx(&full_raw[s], TILE_BYTES + Cfg::B_BYTES);
         uint8_t* rawA = tiles + s * Cfg::RAW_BYTES;
         uint8_t* rawB = rawA + Cfg::OFF_RAW_B;
@@ -621,10 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0 && cta_rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a/b format [7,10)/[10,13) (TF32 = 2,
       // BF16 = 1), majors 15/16, N>>3 [17,23), M>>4 [24,29)
-      auto idesc_of = [&](int pr, uint32_t fmt) {
-        return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn[pr] << 15) | ((uint32_t)p.b_mn[pr] << 16) |
-               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
-      };
+      auto idesc_of = [&](int pr, uint32_t fmt) { return umma_idesc(fmt, p.a_mn[pr], p.b_mn[pr], BM * NCTA, BN); };
       for (int it = 0; it < total; ++it) {
         const int s = it % RS, ph = (it / RS) & 1, pr = it / n_kb;
         const int l = it % LS, phl = (it / LS) & 1;
@@ -654,25 +309,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           umma_commit(&empty_raw[s]);
           umma_commit(&empty_lo[l]);
-        } else if (NCTA == 1 && ACC2) {
-          // two independent accumulation chains, interleaved: the MMA pipe does not have to wait for the previous
-          // read-modify-write of the same TMEM tile before it starts the next instruction
-          const uint32_t d2 = tmem_base + ACC2;
-#pragma unroll
-          for (int ks = 0; ks < BKT / 16; ++ks) {
-            umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], 2 * ks), operand_desc(rawB, p.b_mn[pr], 2 * ks), idesc, (it | ks) != 0);
-            umma_bf16(d2, corr_desc(loA, p.a_mn[pr], ks), corr_desc(hiB, p.b_mn[pr], ks), idesc16, (it | ks) != 0);
-            umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], 2 * ks + 1), operand_desc(rawB, p.b_mn[pr], 2 * ks + 1), idesc, 1);
-            umma_bf16(d2, corr_desc(hiA, p.a_mn[pr], ks), corr_desc(loB, p.b_mn[pr], ks), idesc16, 1);
-          }
-          umma_commit(&empty_raw[s]);
-          umma_commit(&empty_lo[l]);
         } else if (NCTA == 1) {
 #pragma unroll
-          for (int ks = 0; ks < ((HF_TC_VARIANT & 4) ? 0 : BKT / 8); ++ks)
+          for (int ks = 0; ks < BKT / 8; ++ks)
             umma_tf32(tmem_base, operand_desc(rawA, p.a_mn[pr], ks), operand_desc(rawB, p.b_mn[pr], ks), idesc, (it | ks) != 0);
 #pragma unroll
-          for (int ks = 0; ks < ((HF_TC_VARIANT & 4) ? 0 : BKT / 16); ++ks) {
+          for (int ks = 0; ks < BKT / 16; ++ks) {
             umma_bf16(tmem_base, corr_desc(loA, p.a_mn[pr], ks), corr_desc(hiB, p.b_mn[pr], ks), idesc16, 1);
             umma_bf16(tmem_base, corr_desc(hiA, p.a_mn[pr], ks), corr_desc(loB, p.b_mn[pr], ks), idesc16, 1);
           }
@@ -706,7 +348,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (it == 0) tc_mark(2, threadIdx.x == 0, p.trace_epoch);
       if (threadIdx.x == 0) tc_mark_it(trace_it, 1, it);
       const uint32_t st = smem_u32(tiles + s * Cfg::RAW_BYTES), lo = smem_u32(lo_tiles + l * Cfg::LO_BYTES);
-      if (!(HF_TC_VARIANT & 2)) {
       if (TS) {
         const uint32_t a_t = tmem_base + ((uint32_t)(warp * 32) << 16) + BN + l * kTsAcols;
         if (p.a_mn[sp_pr]) split_row_to_tmem<true>(st, a_t, threadIdx.x);
@@ -718,7 +359,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         split_tile<true, Cfg::B_ROWS>(st + Cfg::OFF_RAW_B, lo + Cfg::OFF_B16, lo + Cfg::OFF_B16 + Cfg::B_BYTES / 2);
       else
         split_tile<false, Cfg::B_ROWS>(st + Cfg::OFF_RAW_B, lo + Cfg::OFF_B16, lo + Cfg::OFF_B16 + Cfg::B_BYTES / 2);
-      }
       if (++sp_kb == n_kb) sp_kb = 0, ++sp_pr;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA unit
       __syncwarp();
@@ -743,12 +383,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       float v[16];
       if (total > 0) {
         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
-        if (ACC2) {
-          float v2[16];
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + ACC2 + c, v2);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += v2[j];
-        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -760,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
     tc_mark(5, threadIdx.x == 0, p.trace_epoch);
     float cs[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of what this lane stores (bias gradient of the next layer)
-    epilogue_dispatch(g, stage, m0 + warp * 32, n0 + lane * 4, lane, cs);
+    epilogue_dispatch<LDS_ROW>(g, stage, lane * 4, m0 + warp * 32, n0 + lane * 4, cs);
     if (g.colpart) {
       // 4 warps x 32 rows -> one row of column sums per CTA, fixed order (deterministic)
       float* red = reinterpret_cast<float*>(tiles) + 4 * 32 * (BN + 4);
@@ -823,25 +457,50 @@ bool tc_supported(const GemmArgs& g) {
   return encode_fn() != nullptr;
 }
 
-// 2-D tensor map over one operand.  K-contiguous: dims (K, MN), box (32, 128).  MN-contiguous: dims (MN, K), box (32, 32).
+// Tensor maps are cached by content: the operands of a solve are the same buffers on every CG iteration, so after
+// the first product a launch finds its maps here instead of paying cuTensorMapEncodeTiled four to twelve times.
+struct MapKey {
+  uint64_t w[6];
+  bool operator==(const MapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    for (uint64_t v : k.w) h = (h ^ v) * 0xbf58476d1ce4e5b9ull, h ^= h >> 29;
+    return (size_t)h;
+  }
+};
+
+const CUtensorMap* cached_tensor_map(CUtensorMapDataType dtype, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                                     uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key = {{(uint64_t)(uintptr_t)ptr, dim0, dim1, stride1_bytes, ((uint64_t)box0 << 32) | box1, ((uint64_t)dtype << 32) | (uint64_t)swizzle}};
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  if (cache.size() > 8192) cache.clear();  // pointers of long-dead buffers: start over rather than grow without bound
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {dim0, dim1}, strides[1] = {stride1_bytes};
+  const cuuint32_t box[2] = {box0, box1}, estr[2] = {1, 1};
+  CUresult r = encode_fn()(&map, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (ptr %p dims %llu x %llu stride %llu box %u x %u)", (int)r, ptr,
+              (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)stride1_bytes, box0, box1);
+    return nullptr;
+  }
+  return &cache.emplace(key, map).first->second;
+}
+
+// 2-D tensor map over one FP32 operand.  K-contiguous: dims (K, MN), box (32, rows).  MN-contiguous: dims (MN, K), box (32, 32).
 static int make_map(CUtensorMap* map, const Operand& op, int MN, int K, int box_rows = BM) {
   const bool mn_major = op.s_k != 1;
-  cuuint64_t dims[2], strides[1];
-  cuuint32_t box[2], estr[2] = {1, 1};
-  if (mn_major) {
-    dims[0] = (cuuint64_t)MN, dims[1] = (cuuint64_t)K, strides[0] = (cuuint64_t)op.s_k * 4;
-    box[0] = 32, box[1] = BKT;
-  } else {
-    dims[0] = (cuuint64_t)K, dims[1] = (cuuint64_t)MN, strides[0] = (cuuint64_t)op.s_mn * 4;
-    box[0] = BKT, box[1] = (cuuint32_t)box_rows;
-  }
-  CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(op.ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-                                    : (BKT == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  HF_REQUIRE(r == CUDA_SUCCESS, HF_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  const CUtensorMap* m =
+      mn_major ? cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, op.ptr, (uint64_t)MN, (uint64_t)K, (uint64_t)op.s_k * 4, 32, BKT,
+                                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+               : cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, op.ptr, (uint64_t)K, (uint64_t)MN, (uint64_t)op.s_mn * 4, BKT,
+                                   (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!m) return HF_ERR_CUDA;
+  *map = *m;
   return HF_OK;
 }
 
@@ -882,12 +541,11 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t stream) {
     rc = make_map(&maps[2 * s + 1], g.B[src], g.N, g.K, pair ? BN / 2 : BN);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool seen[64] = {};
+  if (first_use_on_device(seen)) {  // the opt-in is per device: a process may drive several GPUs
     HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_BYTES));
     HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<1>::SMEM_BYTES));
     HF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<2>::SMEM_BYTES));
-    attr_set = true;
   }
   if (pair) {
     cudaLaunchConfig_t cfg = {};

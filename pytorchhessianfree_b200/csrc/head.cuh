@@ -276,11 +276,9 @@ inline bool head_shape_ok(int64_t N, int D, int C, int sms) {
 
 template <int CP>
 inline int launch_head_cp(const HeadArgs& h, const HeadPlan& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool seen[64] = {};
+  if (first_use_on_device(seen))  // the opt-in is per device
     HF_CUDA(cudaFuncSetAttribute(ggn_head_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   ggn_head_kernel<CP><<<p.ctas, kHeadThreads, p.smem, stream>>>(h);
   HF_LAUNCH_CHECK();
   return HF_OK;

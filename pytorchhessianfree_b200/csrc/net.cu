@@ -91,6 +91,7 @@ static inline bool curved(int act) { return act == HF_ACT_SIGMOID || act == HF_A
 // (16 B): TMA needs 16-byte row pitches, and this is what lets the 10-class output layer of the MLP config run on
 // the tensor-core tiles.  The padding columns are never read (all kernels bound their accesses by the width).
 static inline int pad4(int w) { return (w + 3) & ~3; }
+static inline int pad8(int w) { return (w + 7) & ~7; }  // row pitch of the BF16 image planes (16 B)
 
 // ---- row-wise loss kernels ---------------------------------------------------------------------
 
@@ -977,11 +978,18 @@ int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t ac
 int hf_debug_tc_trace(void* d_buf) { return set_tc_trace(d_buf); }
 int hf_debug_tc_trace_iters(void* d_buf) { return set_tc_trace_iters(d_buf); }
 
+size_t hf_contract_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t n_pairs) {
+  // engine 2: two BF16 planes per operand; either orientation of [MN, K] fits in max(rows * pad8(cols))
+  auto planes = [&](int64_t mn) {
+    return 2 * std::max(align_up((size_t)mn * pad8((int)K) * 2, 256), align_up((size_t)K * pad8((int)mn) * 2, 256));
+  };
+  return (size_t)n_pairs * (planes(M) + planes(N));
+}
+
 int hf_contract(int32_t engine, int64_t M, int64_t N, int64_t K, int32_t n_pairs, const hf_operand* A,
                 const hf_operand* B, float* d_C, int64_t ldc, void* d_workspace, size_t workspace_bytes, void* stream) {
   HF_REQUIRE(A && B && d_C && n_pairs >= 1 && n_pairs <= 2, HF_ERR_INVALID, "hf_contract: bad arguments");
   HF_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), HF_ERR_INVALID, "hf_contract: bad shape");
-  (void)d_workspace, (void)workspace_bytes;
   GemmArgs g = blank_gemm();
   g.M = (int)M, g.N = (int)N, g.K = (int)K, g.n_pairs = n_pairs;
   for (int s = 0; s < n_pairs; ++s) {
@@ -989,11 +997,37 @@ int hf_contract(int32_t engine, int64_t M, int64_t N, int64_t K, int32_t n_pairs
     g.B[s] = Operand{B[s].d_ptr, B[s].stride_mn, B[s].stride_k};
   }
   g.C = d_C, g.ldc = ldc, g.epi = EPI_STORE;
+  if (engine == 2 || engine == 3) {  // 3 (profiling): the images are still in the workspace from an identical engine-2 call
+    // pre-split pair engine: the operand images are built in the caller's workspace first (the products keep them
+    // resident instead: hf_lin_forward / the producing epilogues write them)
+    SplitTable t;
+    t.count = 0, t.skip = nullptr;
+    size_t off = 0;
+    char* base = static_cast<char*>(d_workspace);
+    for (int s = 0; s < n_pairs; ++s)
+      for (int which = 0; which < 2; ++which) {
+        Operand& op = which ? g.B[s] : g.A[s];
+        const int64_t mn = which ? N : M;
+        const bool kc = op.s_k == 1;
+        const int64_t rows = kc ? mn : K, cols = kc ? K : mn, ld = kc ? op.s_mn : op.s_k;
+        const int64_t ld16 = pad8((int)cols);
+        const size_t plane_bytes = align_up((size_t)rows * ld16 * 2, 256);
+        HF_REQUIRE(base && off + 2 * plane_bytes <= workspace_bytes, HF_ERR_WORKSPACE,
+                   "hf_contract: engine 2 needs a workspace of at least %zu bytes for the operand images", hf_contract_workspace_bytes(M, N, K, n_pairs));
+        op.img.hi = reinterpret_cast<uint16_t*>(base + off), op.img.plane = (int64_t)(plane_bytes / 2), op.img.ld = ld16;
+        off += 2 * plane_bytes;
+        t.seg[t.count++] = SplitSegment{op.ptr, rows, (int)cols, ld, nullptr, 0, op.img};
+      }
+    int rc = engine == 2 ? launch_split(t, (cudaStream_t)stream) : HF_OK;
+    if (rc) return rc;
+    HF_REQUIRE(tc2_supported(g), HF_ERR_UNSUPPORTED, "hf_contract: shape/alignment not supported by the pre-split tcgen05 engine");
+    return launch_gemm_tc2(g, (cudaStream_t)stream);
+  }
   if (engine == 1) {
     HF_REQUIRE(tc_supported(g), HF_ERR_UNSUPPORTED, "hf_contract: shape/alignment not supported by the tcgen05 engine");
     return launch_gemm_tc(g, (cudaStream_t)stream);
   }
-  HF_REQUIRE(engine == 0, HF_ERR_INVALID, "hf_contract: unknown engine %d", engine);
+  HF_REQUIRE(engine == 0, HF_ERR_INVALID, "hf_contract: unknown engine %d (0 = SIMT, 1 = tcgen05 128x128, 2 = tcgen05 pre-split pairs)", engine);
   return launch_gemm_simt(g, (cudaStream_t)stream);
 }
 

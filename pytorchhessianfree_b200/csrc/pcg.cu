@@ -462,11 +462,9 @@ static int launch_iter(int64_t P, void* d_state, int phase, const void* Bp, cons
                        const void* y_ext, double lambda, void* x, void* r, void* p, void* snapshot, void* p_lo,
                        cudaStream_t stream) {
   const Geometry g = pcg_geometry(P, sizeof(T));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool seen[64] = {};
+  if (first_use_on_device(seen))  // the opt-in is per device
     HF_CUDA(cudaFuncSetAttribute(pcg_iter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResidentBytes));
-    attr_set = true;
-  }
   IterArgs<T> a;
   a.P = P;
   a.groups_per_cta = g.groups_per_cta;

@@ -74,7 +74,9 @@ def lower_loss(loss_func):
 
 
 def _leaves(module):
-    kids = list(module.children())
+    # `_modules`, not `children()`: the latter drops repeated instances, and a Sequential that applies one
+    # `nn.ReLU()` object after every Linear would silently lose all but the first activation
+    kids = [k for k in module._modules.values() if k is not None]
     if not kids:
         yield module
     else:
@@ -82,6 +84,15 @@ def _leaves(module):
             _unsupported(f"container {type(module).__name__} (only nn.Sequential nesting is walked)")
         for k in kids:
             yield from _leaves(k)
+
+
+def _check_param_use(layers, offsets):
+    """Every trainable parameter must feed exactly one layer: the transposed sweep writes each layer's slice of the
+    flat vector once, so a shared weight would have one use overwrite the other."""
+    used = [l.w_offset for l in layers if l.w_offset >= 0] + [l.b_offset for l in layers if l.has_bias and l.b_offset >= 0]
+    if len(used) != len(set(used)):
+        _unsupported("a parameter that is used by more than one layer (weight sharing)")
+    return set(used)
 
 
 def lower_module(model, loss_func, params_list):
@@ -117,8 +128,7 @@ def lower_module(model, loss_func, params_list):
             _unsupported(f"module {type(m).__name__}")
     if not layers:
         _unsupported("a model without Linear layers")
-    used = {l.w_offset for l in layers if l.w_offset >= 0} | {l.b_offset for l in layers if l.has_bias and l.b_offset >= 0}
-    if used != set(offsets.values()):
+    if _check_param_use(layers, offsets) != set(offsets.values()):
         raise ValueError("the optimizer holds trainable parameters that the model does not use")
     return Program(layers, kind, reduction, n_params)
 
@@ -131,16 +141,22 @@ def _name(fn):
     return type(fn).__name__
 
 
-def _leaf_param(fn):
-    """The parameter behind an AccumulateGrad node (through an optional transpose)."""
+def _leaf_param(fn, want_transposed):
+    """The parameter behind an AccumulateGrad node.  ``nn.Linear`` multiplies by ``weight.t()``, so its weight sits
+    behind a TBackward0 node and is read as ``[out, in]``; a bare ``x @ W`` (no transpose) would be read transposed,
+    so it is refused instead.  Biases must come without a transpose."""
     if fn is None:
         return None
-    if _name(fn) == "TBackward0":
+    transposed = _name(fn) == "TBackward0"
+    if transposed:
         fn = fn.next_functions[0][0]
         if fn is None:
             return None
     if _name(fn) != "AccumulateGrad":
         _unsupported(f"a weight produced by {_name(fn)}")
+    if transposed != want_transposed:
+        _unsupported("a matrix product whose weight is not used as `weight.t()` (nn.Linear convention)"
+                     if want_transposed else "a transposed bias")
     return fn.variable
 
 
@@ -193,13 +209,13 @@ def lower_graph(loss, outputs, params_list):
         if nm == "AddmmBackward0":
             if float(node._saved_alpha) != 1.0 or float(node._saved_beta) != 1.0:
                 _unsupported("addmm with alpha/beta != 1")
-            bias, nxt, weight = (_leaf_param(node.next_functions[0][0]), node.next_functions[1][0],
-                                 _leaf_param(node.next_functions[2][0]))
+            bias, nxt, weight = (_leaf_param(node.next_functions[0][0], False), node.next_functions[1][0],
+                                 _leaf_param(node.next_functions[2][0], True))
             saved_in = node._saved_mat1
             if bias is None:
                 _unsupported("a Linear layer with a frozen bias inside the differentiated part of the graph")
         elif nm == "MmBackward0":
-            bias, nxt, weight = None, node.next_functions[0][0], _leaf_param(node.next_functions[1][0])
+            bias, nxt, weight = None, node.next_functions[0][0], _leaf_param(node.next_functions[1][0], True)
             saved_in = node._saved_self
         else:
             _unsupported(f"graph node {nm}")
@@ -217,8 +233,7 @@ def lower_graph(loss, outputs, params_list):
     if pending_act != "none" or not rev or inputs is None:
         _unsupported("a graph that does not end in a Linear layer fed by constant inputs")
     layers = rev[::-1]
-    used = {l.w_offset for l in layers} | {l.b_offset for l in layers if l.has_bias}
-    if used != set(offsets.values()):
+    if _check_param_use(layers, offsets) != set(offsets.values()):
         raise ValueError("One of the optimizer's trainable parameters is not used in the graph of `loss`")
     if inputs.dim() != 2:
         _unsupported("Linear layers applied to inputs that are not [batch, features]")

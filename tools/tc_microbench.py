@@ -1,39 +1,49 @@
+"""Back-to-back launch time of the tensor-tile contractions over shapes, K and operand layouts.
+engine 1 = 128x128 tiles with the in-kernel splitter, engine 2 = 256x256 CTA-pair tiles on pre-split images
+(timed through engine 3: images already built)."""
 import sys, torch
 sys.path[:0] = ['.']
 from pytorchhessianfree_b200 import _lib
 from pytorchhessianfree_b200._lib import Operand
 lib = _lib.load(); dev = 'cuda'
 st = torch.cuda.current_stream().cuda_stream
-def bench(M, N, K, eng, reps=200, layout=(True, True)):
-    a = torch.randn(M, K, device=dev) if layout[0] else torch.randn(K, M, device=dev)
-    b = torch.randn(N, K, device=dev) if layout[1] else torch.randn(K, N, device=dev)
+def bench(M, N, K, eng, reps=100, layout=(True, True), pairs=1):
+    a = [torch.randn(M, K, device=dev) if layout[0] else torch.randn(K, M, device=dev) for _ in range(pairs)]
+    b = [torch.randn(N, K, device=dev) if layout[1] else torch.randn(K, N, device=dev) for _ in range(pairs)]
     c = torch.empty(M, N, device=dev)
-    A = (Operand * 1)(Operand(a.data_ptr(), K, 1) if layout[0] else Operand(a.data_ptr(), 1, M))
-    B = (Operand * 1)(Operand(b.data_ptr(), K, 1) if layout[1] else Operand(b.data_ptr(), 1, N))
+    A = (Operand * pairs)(*[Operand(t.data_ptr(), K, 1) if layout[0] else Operand(t.data_ptr(), 1, M) for t in a])
+    B = (Operand * pairs)(*[Operand(t.data_ptr(), K, 1) if layout[1] else Operand(t.data_ptr(), 1, N) for t in b])
+    nb = lib.hf_contract_workspace_bytes(M, N, K, pairs) if eng >= 2 else 0
+    ws = torch.empty(nb + 256, dtype=torch.uint8, device=dev)
+    wp = (ws.data_ptr() + 255) // 256 * 256
+    if lib.hf_contract(min(eng, 2), M, N, K, pairs, A, B, c.data_ptr(), N, wp, nb, st) != 0:
+        return float('nan')
+    e = 3 if eng == 2 else eng
     for _ in range(5):
-        if lib.hf_contract(eng, M, N, K, 1, A, B, c.data_ptr(), N, None, 0, st) != 0:
-            return float('nan')
+        lib.hf_contract(e, M, N, K, pairs, A, B, c.data_ptr(), N, wp, nb, st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        lib.hf_contract(eng, M, N, K, 1, A, B, c.data_ptr(), N, None, 0, st)
+        lib.hf_contract(e, M, N, K, pairs, A, B, c.data_ptr(), N, wp, nb, st)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / reps
-x = torch.zeros(1024, device=dev)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(200): x.add_(1)
-e1.record(); torch.cuda.synchronize()
-print("tiny torch kernel back-to-back: %.2f us" % (e0.elapsed_time(e1) * 1e3 / 200))
-for (M, N) in [(128, 128), (4096, 512), (4096, 10)]:
-    for K in [32, 64, 128, 256, 512, 1024, 2048]:
-        t = bench(M, N, K, 1)
-        print(f"tc   M={M} N={N} K={K}: {t:7.2f} us   ({2*M*N*K/t/1e6:8.2f} TFLOP/s)")
-for K in [512, 4096]:
-    for lay in [(False, False), (True, False)]:
-        t = bench(512, 784, K, 1, layout=lay)
-        print(f"tc   M=512 N=784 K={K} layout={lay}: {t:7.2f} us ({2*512*784*K/t/1e6:8.2f} TFLOP/s)")
-for (M, N, K) in [(4096, 512, 784), (4096, 10, 512), (4096, 512, 10)]:
-    print(f"simt M={M} N={N} K={K}: {bench(M, N, K, 0, reps=50):7.2f} us")
+KK = (True, True); MM = (False, False); KM = (True, False)
+cases = [  # (M, N, K, layout, pairs, what)
+    (4096, 512, 784, KK, 1, "cfg2 R-op 1"), (4096, 512, 512, KK, 2, "cfg2 R-op 2"), (4096, 512, 512, KM, 1, "cfg2 transposed"),
+    (512, 784, 4096, MM, 1, "cfg2 weight grad 1"),
+    (7500, 1000, 784, KK, 1, "cfg3 R-op 1"), (7500, 500, 1000, KK, 2, "cfg3 R-op 2"), (7500, 784, 1000, KK, 2, "cfg3 R-op 8"),
+    (7500, 1000, 784, KM, 1, "cfg3 transposed 8"), (1000, 784, 7500, MM, 1, "cfg3 weight grad 1 (unsplit)"),
+    (60000, 1000, 784, KK, 1, "cfg3 R-op 1, one 60000 chunk"),
+    (8192, 8192, 2048, KK, 1, "large square"), (16384, 4096, 4096, KK, 1, "large"),
+]
+for M, N, K, lay, pairs, what in cases:
+    f = 2.0 * M * N * K * pairs
+    row = f"{what:32s} M={M:6d} N={N:5d} K={K:5d} x{pairs}:"
+    for eng in (1, 2):
+        t = bench(M, N, K, eng, layout=lay, pairs=pairs)
+        row += f"   engine {eng}: {t:8.2f} us {f / t / 1e6:7.1f} TF/s"
+    print(row, flush=True)
+for K in [32, 256, 1024, 4096]:
+    t1, t2 = bench(9472, 2048, K, 1), bench(9472, 2048, K, 2)   # 37 x 8 pair tiles = 4 full waves of 74 pairs
+    print(f"slope M=9472 N=2048 K={K}: engine 1 {t1:8.2f} us, engine 2 {t2:8.2f} us")
