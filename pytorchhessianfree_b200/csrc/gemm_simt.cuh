@@ -35,6 +35,18 @@ struct Image16 {
   int64_t ld;       // row pitch in elements (multiple of 8)
 };
 
+__device__ __forceinline__ uint16_t bf16_bits(float x) {
+  uint16_t r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+// one element of an image (element-wise kernels; the tile epilogues store four at a time, tc_common.cuh)
+__device__ __forceinline__ void store_image1(const Image16& im, int64_t row, int col, float x) {
+  uint16_t* hi = im.hi + row * im.ld + col;
+  hi[0] = bf16_bits(x);
+  hi[im.plane] = bf16_bits(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
+
 struct Operand {
   const float* ptr;
   int64_t s_mn;

@@ -72,6 +72,19 @@ struct hf_lin {
   // tensor engine reads 16-byte-pitched copies instead.  wpad[l] is refreshed by hf_lin_forward (weights are fixed
   // for the life of a linearisation), vpad[l] at the start of every product.
   std::vector<float*> wpad, vpad;
+  // Split-precision images (gemm_simt.cuh: Image16) for the pre-split pair engine: one per library-owned [rows, width]
+  // matrix that a contraction may read, looked up by the FP32 base pointer.  Constant operands (inputs, activations,
+  // weights) are split once in hf_lin_forward, the CG direction once per product, tangents and cotangents by the
+  // epilogue of the kernel that produces them.
+  struct ImgBuf {
+    const float* base;
+    uint16_t* hi;
+    int64_t plane;  // elements between the hi and the lo plane
+  };
+  bool use_images;
+  std::vector<ImgBuf> imgs;
+  ImgBuf x_img;
+  std::vector<ImgBuf> w_img, v_img;  // per layer; base filled in when the parameter / direction pointer is known
   const float* pending_cur;   // phased sweep: cotangent of the first trainable layer, left by phase 0 for phase 1
   int pending_cols;
   cudaStream_t side;          // weight/bias gradients of layer l run here, concurrently with the data product that
@@ -93,6 +106,29 @@ static inline bool curved(int act) { return act == HF_ACT_SIGMOID || act == HF_A
 static inline int pad4(int w) { return (w + 3) & ~3; }
 static inline int pad8(int w) { return (w + 7) & ~7; }  // row pitch of the BF16 image planes (16 B)
 
+// the image of the library-owned matrix at `base`, read as rows of `width` elements (nullptr image if there is none)
+static Image16 image_for(const hf_lin* lin, const float* base, int width) {
+  Image16 im = {nullptr, 0, 0};
+  if (!lin->use_images || !base) return im;
+  auto hit = [&](const hf_lin::ImgBuf& b) {
+    if (b.base != base || !b.hi) return false;
+    im.hi = b.hi, im.plane = b.plane, im.ld = pad8(width);
+    return true;
+  };
+  if (hit(lin->x_img)) return im;
+  for (const auto& b : lin->imgs)
+    if (hit(b)) return im;
+  for (const auto& b : lin->w_img)
+    if (hit(b)) return im;
+  for (const auto& b : lin->v_img)
+    if (hit(b)) return im;
+  return im;
+}
+static Operand with_image(const hf_lin* lin, Operand op, int width) {
+  op.img = image_for(lin, op.ptr, width);
+  return op;
+}
+
 // ---- row-wise loss kernels ---------------------------------------------------------------------
 
 struct LossArgs {
@@ -105,6 +141,7 @@ struct LossArgs {
   float scale;    // 1/n_total (ce mean), 1/(n_total*C) (mse/bce mean), 1 (sum)
   float* prob;    // may be null
   float* delta;   // may be null: dloss/dz_L (through the final activation)
+  Image16 delta_img;  // optional split image of delta (operand of the gradient sweep on the pair engine)
   double* partial;
 };
 
@@ -130,7 +167,11 @@ __global__ void __launch_bounds__(256) loss_forward_kernel(LossArgs a) {
       for (int c = lane; c < a.C; c += 32) {
         const float p = expf(z[c] - lse);
         if (a.prob) a.prob[n * a.ld + c] = p;
-        if (a.delta) a.delta[n * a.ld + c] = a.scale * (p - (c == t ? 1.f : 0.f));
+        if (a.delta) {
+          const float d = a.scale * (p - (c == t ? 1.f : 0.f));
+          a.delta[n * a.ld + c] = d;
+          if (a.delta_img.hi) store_image1(a.delta_img, n, c, d);
+        }
       }
       row = (t >= 0 && t < a.C) ? (lse - z[t]) : 0.f;  // every lane holds the same value
     } else {
@@ -149,7 +190,11 @@ __global__ void __launch_bounds__(256) loss_forward_kernel(LossArgs a) {
           d = p - tc;
           if (a.prob) a.prob[n * a.ld + c] = p;
         }
-        if (a.delta) a.delta[n * a.ld + c] = a.scale * d * act_d1(a.final_act, zc);
+        if (a.delta) {
+          const float dz = a.scale * d * act_d1(a.final_act, zc);
+          a.delta[n * a.ld + c] = dz;
+          if (a.delta_img.hi) store_image1(a.delta_img, n, c, dz);
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -191,6 +236,7 @@ struct HessArgs {
   int splits;
   int64_t part_stride;
   const float* bias;
+  Image16 img;  // optional: split image of u (the transposed sweep reads u as a tensor-engine operand)
 };
 
 __global__ void __launch_bounds__(256) loss_hessian_kernel(HessArgs a) {
@@ -222,6 +268,8 @@ __global__ void __launch_bounds__(256) loss_hessian_kernel(HessArgs a) {
       const float* p = a.prob + n * a.ld;
       for (int c = lane; c < a.C; c += 32) r[c] = a.scale * p[c] * (1.f - p[c]) * r[c];
     }
+    if (a.img.hi)
+      for (int c = lane; c < a.C; c += 32) store_image1(a.img, n, c, r[c]);  // each lane re-reads its own columns
   }
 }
 
@@ -235,38 +283,22 @@ static inline const float* bias_ptr(const Layer& l, const float* theta) {
   return l.b_off >= 0 ? theta + l.b_off : l.b_frozen;
 }
 
-// dst[r][0..ld) = src[r][0..cols) padded with zeros
-__global__ void pitch_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int ld,
-                                  const int32_t* __restrict__ skip) {
-  if (skip && *skip) return;
-  const int64_t total = (int64_t)rows * ld;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / ld), c = (int)(i % ld);
-    dst[i] = c < cols ? src[(int64_t)r * cols + c] : 0.f;
-  }
-}
-
-static int pitch_rows(const float* src, float* dst, int rows, int cols, const int32_t* skip, cudaStream_t stream) {
-  const int ld = pad4(cols);
-  int64_t blocks = ((int64_t)rows * ld + 255) / 256;
-  if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
-  pitch_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, rows, cols, ld, skip);
-  HF_LAUNCH_CHECK();
-  return HF_OK;
-}
-
 // weight / direction operand of layer l as the kernels should read it: in place, or the 16-byte-pitched copy
 static inline Operand w_operand(const hf_lin* lin, int l, const float* theta, bool k_contig) {
   const Layer& L = lin->net->L[l];
   const float* p = lin->wpad[l] ? lin->wpad[l] : weight_ptr(L, theta);
   const int ld = lin->wpad[l] ? pad4(L.in) : L.in;
-  return k_contig ? Operand{p, ld, 1} : Operand{p, 1, ld};
+  Operand op = k_contig ? Operand{p, ld, 1} : Operand{p, 1, ld};
+  if (lin->use_images && lin->w_img[l].hi) op.img = Image16{lin->w_img[l].hi, lin->w_img[l].plane, pad8(L.in)};
+  return op;
 }
 static inline Operand v_operand(const hf_lin* lin, int l, const float* v, bool k_contig) {
   const Layer& L = lin->net->L[l];
   const float* p = lin->vpad[l] ? lin->vpad[l] : v + L.w_off;
   const int ld = lin->vpad[l] ? pad4(L.in) : L.in;
-  return k_contig ? Operand{p, ld, 1} : Operand{p, 1, ld};
+  Operand op = k_contig ? Operand{p, ld, 1} : Operand{p, 1, ld};
+  if (lin->use_images && lin->v_img[l].hi) op.img = Image16{lin->v_img[l].hi, lin->v_img[l].plane, pad8(L.in)};
+  return op;
 }
 
 struct SplitPlan {
@@ -304,6 +336,23 @@ static SplitPlan plan_split(int M, int N, int64_t K, bool tensor_tiles) {
   return p;
 }
 
+// The same for the 256x256 CTA-pair tiles: the split count that minimises waves x k-blocks, subject to the 1024-sample
+// accumulation rule above.  `us` receives the modelled time (gemm_tc.cuh: tc2_estimate).
+static SplitPlan plan_split_pair(int M, int N, int64_t K, double* us) {
+  const int64_t ktiles = (K + 31) / 32;
+  const int64_t lo = std::max<int64_t>(1, (ktiles + 31) / 32), hi = std::max<int64_t>(lo, std::min<int64_t>(64, ktiles / 4));
+  SplitPlan best = {1, (int)(ktiles * 32)};
+  double best_us = 1e30;
+  for (int64_t want = lo; want <= hi; ++want) {
+    const int64_t kt_per = (ktiles + want - 1) / want;
+    const int splits = (int)((ktiles + kt_per - 1) / kt_per);
+    const double t = tc2_estimate(M, N, (int)K, 1, splits).us_pair + 0.05 * splits;  // the reduction reads every partial
+    if (t < best_us) best_us = t, best = SplitPlan{splits, (int)(kt_per * 32)};
+  }
+  if (us) *us = best_us;
+  return best;
+}
+
 // would a weight-gradient contraction [out,in] over `batch` samples run on the tensor-core tiles?
 static bool weight_on_tensor(const hf_net* net, int out, int in, int64_t batch, int square) {
   return net->engine == 1 && !square && in % 4 == 0 && (int64_t)out * in * batch >= kTcMinWork;
@@ -327,11 +376,31 @@ static GemmArgs blank_gemm() {
   return g;
 }
 
-// dispatch one contraction to the tensor-core engine when the net asks for it and the shape fits
-static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream, bool* on_tensor = nullptr) {
-  const bool tc = net->engine == 1 && tc_supported(g);
+// should this contraction (operand images present) run on the CTA-pair tiles rather than the 128x128 tiles?
+static bool prefer_pair(const GemmArgs& g) {
+  if (tc2_mode() == 0 || !tc2_supported(g)) return false;
+  if (tc2_mode() == 2) return true;
+  if ((int64_t)g.M * g.N * g.K < kTcMinWork || g.N < 96 || g.M < 192) return false;  // narrow tiles are mostly padding
+  const Tc2Choice c = tc2_estimate(g.M, g.N, g.K, g.n_pairs, std::max(1, g.split_k));
+  return c.us_pair < 0.9 * c.us_single;
+}
+
+// Dispatch one contraction: CTA-pair tensor tiles on pre-split images where they exist and pay, 128x128 tensor tiles
+// where the shape meets the TMA rules, FP32 SIMT tiles otherwise.  Whichever engine runs, the split image of C is
+// written when the caller asks for one (g.c_img): by the tensor engines' epilogues, or by a split pass after the
+// SIMT kernel.
+static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream, bool* on_tensor = nullptr, int pair_hint = -1) {
+  const bool pair = net->engine == 1 && (pair_hint < 0 ? prefer_pair(g) : pair_hint == 1);
+  const bool tc = net->engine == 1 && (pair || tc_supported(g));
   if (on_tensor) *on_tensor = tc;
-  return tc ? launch_gemm_tc(g, stream) : launch_gemm_simt(g, stream);
+  if (pair) return launch_gemm_tc2(g, stream);
+  if (tc) return launch_gemm_tc(g, stream);
+  int rc = launch_gemm_simt(g, stream);
+  if (rc || !g.c_img.hi || g.split_k > 1) return rc;
+  SplitTable t;
+  t.count = 1, t.skip = g.skip;
+  t.seg[0] = SplitSegment{g.C, g.M, g.N, g.ldc, nullptr, 0, g.c_img};
+  return launch_split(t, stream);
 }
 
 // Gradient slices of one layer: out_W[out,in] (+)= scale * sum_pairs A_s^T B_s over the batch (split-K partials),
@@ -344,18 +413,26 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
   int splits_w = 0, splits_b = 0;
   float* const partial = main_scratch ? lin->partial_main : lin->partial;
   if (out_w) {
-    const SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, square));
-    HF_REQUIRE((size_t)sp.splits * M * N <= (main_scratch ? lin->partial_main_floats : lin->partial_floats), HF_ERR_WORKSPACE,
-               "split-K scratch too small");
     GemmArgs g = blank_gemm();
     g.M = M, g.N = N, g.K = (int)lin->N, g.n_pairs = n_pairs;
     for (int s = 0; s < n_pairs; ++s) g.A[s] = A[s], g.B[s] = B[s];
     g.square = square;
+    SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, square));
+    int pair_hint = 0;
+    if (lin->net->engine == 1 && tc2_mode() != 0 && tc2_supported(g)) {
+      // both engines can take it: compare the modelled times of their own best split
+      double us_pair = 0.0;
+      const SplitPlan sp2 = plan_split_pair(M, N, lin->N, &us_pair);
+      const double us_single = tc2_estimate(M, N, (int)lin->N, 1, sp.splits).us_single + 0.05 * sp.splits;
+      if (tc2_mode() == 2 || us_pair < 0.9 * us_single) sp = sp2, pair_hint = 1;
+    }
+    HF_REQUIRE((size_t)sp.splits * M * N <= (main_scratch ? lin->partial_main_floats : lin->partial_floats), HF_ERR_WORKSPACE,
+               "split-K scratch too small");
     g.C = partial, g.ldc = N;
     g.epi = EPI_STORE;
     g.split_k = sp.splits, g.k_per_split = sp.k_per_split;
     g.skip = skip;
-    int rc = run_gemm(lin->net, g, stream);
+    int rc = run_gemm(lin->net, g, stream, nullptr, pair_hint);
     if (rc) return rc;
     splits_w = sp.splits;
   }
@@ -387,6 +464,30 @@ static float loss_scale(const hf_net* net, int64_t n_total) {
   return (float)(1.0 / ((double)n_total * (double)net->classes));
 }
 
+// Operand forms of the direction v for layers [l_begin, l_end): the 16-byte-pitched FP32 copy where the flat slice
+// cannot be addressed by TMA in place, and the split-precision image for the pair engine -- all layers in one launch.
+static int prepare_direction(hf_lin* lin, const float* v, int l_begin, int l_end, const int32_t* skip, cudaStream_t stream) {
+  const hf_net* net = lin->net;
+  SplitTable t;
+  t.count = 0, t.skip = skip;
+  for (int l = l_begin; l < l_end; ++l) {
+    const Layer& L = net->L[l];
+    if (L.w_off < 0) continue;
+    hf_lin::ImgBuf& vi = lin->v_img[l];
+    const bool img = lin->use_images && vi.hi;
+    if (!lin->vpad[l] && !img) continue;
+    if (img) vi.base = lin->vpad[l] ? lin->vpad[l] : v + L.w_off;
+    t.seg[t.count++] = SplitSegment{v + L.w_off, L.out, L.in, L.in, lin->vpad[l], pad4(L.in),
+                                    img ? Image16{vi.hi, vi.plane, pad8(L.in)} : Image16{nullptr, 0, 0}};
+    if (t.count == kMaxSplitSegments) {
+      int rc = launch_split(t, stream);
+      if (rc) return rc;
+      t.count = 0;
+    }
+  }
+  return launch_split(t, stream);
+}
+
 // R-op forward: R{output} = J v into lin->buf[which]; returns the buffer index holding it
 // (with `below_head` the last layer is left to the fused head and *below_head receives R{a_{L-2}})
 static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hessian, const int32_t* skip,
@@ -396,11 +497,8 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
   const int l_end = nl - (below_head ? 1 : 0);
   const float* cur = nullptr;
   int which = 0;
-  for (int l = net->first_trainable; l < l_end; ++l)
-    if (lin->vpad[l]) {
-      int rc = pitch_rows(v + net->L[l].w_off, lin->vpad[l], net->L[l].out, net->L[l].in, skip, stream);
-      if (rc) return rc;
-    }
+  int rcp = prepare_direction(lin, v, net->first_trainable, l_end, skip, stream);
+  if (rcp) return rcp;
   for (int l = net->first_trainable; l < l_end; ++l) {
     const Layer& L = net->L[l];
     const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
@@ -409,11 +507,11 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
     g.M = (int)lin->N, g.N = L.out, g.K = L.in;
     int np = 0;
     if (L.w_off >= 0) {
-      g.A[np] = op_kc(a_in, ld_in), g.B[np] = v_operand(lin, l, v, true);
+      g.A[np] = with_image(lin, op_kc(a_in, ld_in), L.in), g.B[np] = v_operand(lin, l, v, true);
       ++np;
     }
     if (cur) {
-      g.A[np] = op_kc(cur, ld_in), g.B[np] = w_operand(lin, l, theta, true);
+      g.A[np] = with_image(lin, op_kc(cur, ld_in), L.in), g.B[np] = w_operand(lin, l, theta, true);
       ++np;
     }
     float* dst = (hessian && l < nl - 1) ? lin->ra[l] : lin->buf[which];
@@ -442,6 +540,11 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
     if (np == 0) {
       // a frozen layer fed by a zero tangent contributes only its (frozen) nothing: R{z} = 0
       HF_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * lin->N * ld_out, stream));
+      const Image16 im = image_for(lin, dst, L.out);
+      if (im.hi) {
+        HF_CUDA(cudaMemsetAsync(im.hi, 0, sizeof(uint16_t) * lin->N * im.ld, stream));
+        HF_CUDA(cudaMemsetAsync(im.hi + im.plane, 0, sizeof(uint16_t) * lin->N * im.ld, stream));
+      }
     } else {
       g.n_pairs = np;
       g.C = dst, g.ldc = ld_out;
@@ -449,6 +552,7 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
       g.bias = (L.has_bias && L.b_off >= 0) ? v + L.b_off : nullptr;
       g.aux = lin->a[l], g.ldaux = ld_out;
       g.C2 = (hessian && curved(L.act)) ? lin->rz[l] : nullptr;
+      g.c_img = image_for(lin, dst, L.out);  // the next layer's R-op (or the transposed sweep) reads it as an operand
       g.skip = skip;
       int rc = run_gemm(net, g, stream);
       if (rc) return rc;
@@ -469,6 +573,7 @@ static int apply_loss_hessian(hf_lin* lin, float* rz, const int32_t* skip, cudaS
   h.N = lin->N, h.C = net->classes, h.ld = pad4(net->classes), h.loss = net->loss, h.final_act = net->L.back().act;
   h.scale = loss_scale(net, lin->n_total);
   h.skip = skip;
+  h.img = image_for(lin, rz, net->classes);
   h.part = lin->fwd_splits > 0 ? lin->partial_fwd : nullptr;
   h.splits = lin->fwd_splits, h.part_stride = lin->N * (int64_t)pad4(net->classes), h.bias = lin->fwd_bias;
   int64_t blocks = (lin->N + 7) / 8;
@@ -500,7 +605,13 @@ static int ggn_head(hf_lin* lin, const float* theta, const float* v, const float
   h.scale = loss_scale(net, lin->n_total);
   h.rows_per_cta = lin->head.rows_per_cta;
   h.skip = skip;
-  return launch_head(h, lin->head, stream);
+  int rc = launch_head(h, lin->head, stream);
+  const Image16 img = image_for(lin, h.cot, L.in);
+  if (rc || !img.hi) return rc;
+  SplitTable t;  // the head kernel stores FP32 only: give the pair engine its operand forms of cot[L-2]
+  t.count = 1, t.skip = skip;
+  t.seg[0] = SplitSegment{h.cot, lin->N, L.in, pad4(L.in), nullptr, 0, img};
+  return launch_split(t, stream);
 }
 
 enum BackMode { BACK_GRADIENT, BACK_GGN, BACK_FISHER, BACK_HESSIAN };
@@ -560,7 +671,7 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
     {
       Operand A[2], B[2];
       int np = 0;
-      A[np] = op_mnc(cur, ld_out), B[np] = op_mnc(a_in, ld_in), ++np;
+      A[np] = with_image(lin, op_mnc(cur, ld_out), L.out), B[np] = with_image(lin, op_mnc(a_in, ld_in), L.in), ++np;
       if (mode == BACK_HESSIAN && l > net->first_trainable) {
         A[np] = op_mnc(lin->delta[l], ld_out), B[np] = op_mnc(lin->ra[l - 1], ld_in), ++np;
       }
@@ -580,13 +691,14 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       GemmArgs g = blank_gemm();
       g.M = (int)lin->N, g.N = L.in, g.K = L.out;
       int np = 0;
-      g.A[np] = op_kc(cur, ld_out), g.B[np] = w_operand(lin, l, theta, false), ++np;
+      g.A[np] = with_image(lin, op_kc(cur, ld_out), L.out), g.B[np] = w_operand(lin, l, theta, false), ++np;
       if (mode == BACK_HESSIAN && L.w_off >= 0) {
         g.A[np] = op_kc(lin->delta[l], ld_out), g.B[np] = v_operand(lin, l, v, false), ++np;
       }
       g.n_pairs = np;
       float* dst = keep ? lin->delta[l - 1] : lin->cot[l - 1];
       g.C = dst, g.ldc = ld_in;
+      g.c_img = image_for(lin, dst, L.in);  // operand of the next product down the sweep (kept current in every mode)
       g.act = Lp.act;
       g.aux = lin->a[l - 1], g.ldaux = ld_in;
       if (mode == BACK_HESSIAN) {
@@ -675,6 +787,28 @@ static void release_async(hf_lin* lin) {
   if (lin->side) cudaStreamDestroy(lin->side), lin->side = nullptr;
 }
 
+// the largest split count any engine's plan may ask for on a weight-gradient contraction (sizes the partial-tile scratch)
+static int max_weight_splits(const hf_net* net, int out, int in, int64_t N, bool images) {
+  int splits = plan_split(out, in, N, false).splits;
+  if (weight_on_tensor(net, out, in, N, 0)) splits = std::max(splits, plan_split(out, in, N, true).splits);
+  if (images) splits = std::max(splits, plan_split_pair(out, in, N, nullptr).splits);
+  return splits;
+}
+
+// Does this net at this chunk size have a contraction the CTA-pair engine wins?  Then the linearisation keeps the
+// split-precision images of its operands (twice the activation memory) and the epilogues emit them.
+static bool wants_images(const hf_net* net, int64_t N, int flags) {
+  if (net->engine != 1 || tc2_mode() == 0 || (flags & HF_LIN_LOSS_ONLY)) return false;
+  if (tc2_mode() == 2) return true;
+  for (int l = net->first_trainable; l < (int)net->L.size(); ++l) {
+    const Layer& L = net->L[l];
+    if ((int64_t)N * L.out * L.in < kTcMinWork || L.out < 96 || N < 192) continue;
+    const Tc2Choice c = tc2_estimate((int)N, L.out, L.in, 1, 1);
+    if (c.us_pair < 0.8 * c.us_single) return true;
+  }
+  return false;
+}
+
 // one pass over the carve-up: either measures (base == nullptr) or assigns pointers
 static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin* lin) {
   size_t off = 0;
@@ -685,6 +819,7 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   };
   const int nl = (int)net->L.size();
   const bool hess = flags & HF_LIN_HESSIAN, loss_only = flags & HF_LIN_LOSS_ONLY;
+  const bool images = wants_images(net, N, flags);
   if (lin) lin->a.assign(nl, nullptr), lin->delta.assign(nl, nullptr), lin->ga.assign(nl, nullptr),
       lin->ra.assign(nl, nullptr), lin->rz.assign(nl, nullptr);
   if (loss_only) {
@@ -712,20 +847,14 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   if (!loss_only)
     for (int l = net->first_trainable; l < nl; ++l) {
       const Layer& L = net->L[l];
-      if (L.w_off >= 0) {
-        const int splits = std::max(plan_split(L.out, L.in, N, false).splits,
-                                    weight_on_tensor(net, L.out, L.in, N, 0) ? plan_split(L.out, L.in, N, true).splits : 1);
-        pf = std::max(pf, (size_t)splits * L.out * L.in);
-      }
+      if (L.w_off >= 0) pf = std::max(pf, (size_t)max_weight_splits(net, L.out, L.in, N, images) * L.out * L.in);
       pf = std::max(pf, (size_t)colsum_plan(N) * L.out);
     }
   float* part = pf ? (float*)take(sizeof(float) * pf) : nullptr;
   size_t pf_main = 0;
   if (!loss_only && net->L[net->first_trainable].w_off >= 0 && net->first_trainable < nl - 1) {
     const Layer& L = net->L[net->first_trainable];
-    const int splits = std::max(plan_split(L.out, L.in, N, false).splits,
-                                weight_on_tensor(net, L.out, L.in, N, 0) ? plan_split(L.out, L.in, N, true).splits : 1);
-    pf_main = (size_t)splits * L.out * L.in;
+    pf_main = (size_t)max_weight_splits(net, L.out, L.in, N, images) * L.out * L.in;
   }
   float* part_main = pf_main ? (float*)take(sizeof(float) * pf_main) : nullptr;
   const int fwd_max = (!loss_only && net->classes <= 32) ? 16 : 0;
@@ -762,6 +891,39 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       float* ct = l < nl - 1 ? (float*)take(sizeof(float) * N * pad4(net->L[l].out)) : nullptr;
       if (lin) lin->colbuf[l] = cb, lin->cot[l] = ct;
     }
+  // split-precision images: two BF16 planes per matrix, row pitch pad8(width)
+  if (lin) lin->use_images = images, lin->imgs.clear(), lin->x_img = {nullptr, nullptr, 0},
+           lin->w_img.assign(nl, {nullptr, nullptr, 0}), lin->v_img.assign(nl, {nullptr, nullptr, 0});
+  if (images) {
+    auto take_img = [&](const float* fp32, int64_t rows, int width) {
+      const size_t plane = align_up((size_t)rows * pad8(width) * 2, 256);
+      uint16_t* hi = (uint16_t*)take(2 * plane);
+      return hf_lin::ImgBuf{fp32, hi, (int64_t)(plane / 2)};
+    };
+    const hf_lin::ImgBuf xi = take_img(nullptr, N, net->L[0].in);  // base = the caller's inputs, known at forward time
+    if (lin) lin->x_img = xi;
+    for (int l = 0; l < nl - 1; ++l) {
+      const hf_lin::ImgBuf b = take_img(lin ? lin->a[l] : nullptr, N, net->L[l].out);
+      if (lin) lin->imgs.push_back(b);
+    }
+    for (int i = 0; i < 2; ++i) {
+      const hf_lin::ImgBuf b = take_img(i ? b1 : b0, N, net->max_width);
+      if (lin) lin->imgs.push_back(b);
+    }
+    const hf_lin::ImgBuf dl = take_img(dL, N, net->classes);
+    if (lin) lin->imgs.push_back(dl);
+    for (int l = net->first_trainable; l < nl; ++l) {
+      const Layer& L = net->L[l];
+      if (l < nl - 1) {
+        const hf_lin::ImgBuf b = take_img(lin ? lin->cot[l] : nullptr, N, L.out);
+        if (lin) lin->imgs.push_back(b);
+      }
+      const hf_lin::ImgBuf wi = take_img(nullptr, L.out, L.in);
+      hf_lin::ImgBuf vi = {nullptr, nullptr, 0};
+      if (L.w_off >= 0) vi = take_img(nullptr, L.out, L.in);
+      if (lin) lin->w_img[l] = wi, lin->v_img[l] = vi;
+    }
+  }
   int64_t lb = (N + 7) / 8;
   if (lb > 1024) lb = 1024;
   double* lp = (double*)take(sizeof(double) * lb);
@@ -843,10 +1005,6 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     g.A[0] = op_kc(l == 0 ? d_x : lin->a[l - 1], l == 0 ? L.in : pad4(L.in));
     g.B[0] = op_kc(weight_ptr(L, d_theta), L.in);
     g.C = lin->a[l], g.ldc = pad4(L.out);
-    if (lin->wpad[l]) {  // weights are fixed from here on: refresh the 16-byte-pitched copy the tensor engine reads
-      int rcp = pitch_rows(weight_ptr(L, d_theta), lin->wpad[l], L.out, L.in, nullptr, stream);
-      if (rcp) return rcp;
-    }
     g.epi = EPI_BIAS_ACT, g.act = L.act, g.bias = bias_ptr(L, d_theta);
     // The linearisation point fixes the ReLU masks for the whole solve, so it is evaluated in plain FP32: the
     // ~5e-6 error of the split-precision tensor tiles would flip a few dozen of the 4M masks of the MLP config (each flip moves a
@@ -855,11 +1013,44 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     int rc = (lin->flags & HF_LIN_LOSS_ONLY) ? run_gemm(net, g, stream) : launch_gemm_simt(g, stream);
     if (rc) return rc;
   }
+  {
+    // Operand forms of everything that stays constant for the life of this linearisation, in one launch: the
+    // 16-byte-pitched FP32 copies of weights whose flat slice TMA cannot address in place, and (pair engine) the
+    // split-precision images of the inputs, the activations and the weights.
+    SplitTable t;
+    t.count = 0, t.skip = nullptr;
+    auto push = [&](const SplitSegment& sg) -> int {
+      t.seg[t.count++] = sg;
+      if (t.count < kMaxSplitSegments) return HF_OK;
+      int rc = launch_split(t, stream);
+      t.count = 0;
+      return rc;
+    };
+    const Image16 none = {nullptr, 0, 0};
+    int rc = HF_OK;
+    if (lin->use_images) {
+      lin->x_img.base = d_x;
+      rc = push(SplitSegment{d_x, lin->N, net->L[0].in, net->L[0].in, nullptr, 0, image_for(lin, d_x, net->L[0].in)});
+      for (int l = 0; l < nl - 1 && !rc; ++l)
+        rc = push(SplitSegment{lin->a[l], lin->N, net->L[l].out, pad4(net->L[l].out), nullptr, 0, image_for(lin, lin->a[l], net->L[l].out)});
+    }
+    for (int l = net->first_trainable; l < nl && !rc && !(lin->flags & HF_LIN_LOSS_ONLY); ++l) {
+      const Layer& L = net->L[l];
+      const bool img = lin->use_images && lin->w_img[l].hi;
+      if (!lin->wpad[l] && !img) continue;
+      if (img) lin->w_img[l].base = lin->wpad[l] ? lin->wpad[l] : weight_ptr(L, d_theta);
+      rc = push(SplitSegment{weight_ptr(L, d_theta), L.out, L.in, L.in, lin->wpad[l], pad4(L.in),
+                             img ? Image16{lin->w_img[l].hi, lin->w_img[l].plane, pad8(L.in)} : none});
+    }
+    if (!rc) rc = launch_split(t, stream);
+    if (rc) return rc;
+  }
   LossArgs a;
   a.out = lin->a.back(), a.target = d_targets, a.N = lin->N, a.C = net->classes, a.ld = pad4(net->classes);
   a.loss = net->loss, a.final_act = net->L.back().act;
   a.scale = loss_scale(net, n_total);
   a.prob = lin->prob, a.delta = lin->deltaL, a.partial = lin->loss_partial;
+  a.delta_img = image_for(lin, lin->deltaL, net->classes);
   int64_t blocks = (lin->N + 7) / 8;
   if (blocks > lin->loss_blocks) blocks = lin->loss_blocks;
   loss_forward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
