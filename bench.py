@@ -1,19 +1,23 @@
-"""Benchmark of the hot path: fixed-K preconditioned-CG solves with GGN-vector products on the
-BASELINE.json configs[1] workload (MLP 784-512-512-10 ReLU, CrossEntropy, batch 4096 per GPU,
-Fisher-diagonal PCG).
+"""Benchmark of the hot path on the workload BASELINE.json quotes its scaling metric on (configs[2]):
+fixed-K preconditioned-CG solves with GGN-vector products on Martens' deep autoencoder
+784-1000-500-250-30-250-500-1000-784 (sigmoid units, linear code layer, BCE-with-logits, mean reduction),
+batch 60 000 as 8 `acc_step` chunks of 7 500, chunk c on rank c mod N.
 
     python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's sm_100a path
     python bench.py --impl reference --steps 5 --warmup 1     # the CPU oracle port of the reference path
-    torchrun --nproc-per-node N ... bench.py --gpus N ...     # batch sharded over N ranks (weak scaling)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # the same 60 000 samples sharded over N ranks (strong scaling)
 
-One "step" = one PCG solve of (G + lambda I) x = -g with exactly K_cg = 50 iterations (tol = 0, Martens'
-criterion off, so only the iteration cap stops it -- BASELINE.md section 3; all termination quantities are
-still computed every iteration).  Each iteration = one GGN-vector product over the rank's 4096-sample
-shard (+ one all-reduce of the P-vector when N > 1) + one fused CG vector update.  The unit counted is
-that per-shard product, so `value` = steps * K_cg * N / seconds.
+One "step" = one PCG solve of (G + lambda I) x = -g with exactly K_cg = 50 iterations (tol = 0, Martens' criterion
+off, so only the iteration cap stops it -- BASELINE.md section 3; all termination quantities are still computed every
+iteration).  Each iteration = one GGN-vector product over the WHOLE 60 000-sample batch (the rank's chunks, then one
+all-reduce of the P-vector when N > 1) + one fused CG vector update.  The unit counted is that full-batch product, so
+`value` = steps * K_cg / seconds at every N ("scaling": "strong").
 
-Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream around every step, max over
-ranks, L2 flushed (256 MiB write) between steps outside the timed region.
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream around every step, max over ranks, L2
+flushed (256 MiB write) between steps outside the timed region.  Extra blocks: `e2e` (host buffers in, Newton step
+out), `e2e_api` (HessianFree.get_preconditioner + acc_step on host tensors), `roofline` (dominant contraction timed
+alone), `roofline_cg_update`, `allreduce`, `cfg2` (the round-1 workload, BASELINE.json configs[1], N = 1 only),
+`cpu_baseline`.
 """
 import argparse
 import json
@@ -28,34 +32,58 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WIDTHS = [784, 512, 512, 10]
-BATCH = 4096
+AE_WIDTHS = [784, 1000, 500, 250, 30, 250, 500, 1000, 784]
+AE_LINEAR_AFTER = 3          # the 30-unit code layer is linear (Martens 2010)
+BATCH, CHUNKS = 60000, 8     # 7 500 samples per chunk = the per-GPU shard at 8 GPUs
+MLP_WIDTHS, MLP_BATCH = [784, 512, 512, 10], 4096   # BASELINE.json configs[1] (extra block)
 K_CG = 50
 DAMPING = 1e-3  # small enough that 50 iterations stay clear of the float32 rounding floor (with lambda = 1 the
 #                 solve converges in ~13 iterations and a fixed-50 run would divide 0/0)
 METRIC = "GGN-vector products/sec (CG iters/sec)"
 UNIT = "products/s"
+WORKLOAD = "martens_ae_784-1000-500-250-30-250-500-1000-784_sigmoid_bce_batch60000_ggn_fisher_pcg"
 
 
-def build_mlp(seed=0):
+def build_net(widths, act, linear_after=(), seed=0):
     torch.manual_seed(seed)
     mods = []
-    for i in range(len(WIDTHS) - 1):
-        mods.append(torch.nn.Linear(WIDTHS[i], WIDTHS[i + 1]))
-        if i < len(WIDTHS) - 2:
-            mods.append(torch.nn.ReLU())
+    for i in range(len(widths) - 1):
+        mods.append(torch.nn.Linear(widths[i], widths[i + 1]))
+        if i < len(widths) - 2 and i not in linear_after:
+            mods.append(act())
     return torch.nn.Sequential(*mods)
 
 
-def synth(seed, n=BATCH):
+def build_ae(seed=0):
+    return build_net(AE_WIDTHS, torch.nn.Sigmoid, (AE_LINEAR_AFTER,), seed)
+
+
+def build_mlp(seed=0):
+    return build_net(MLP_WIDTHS, torch.nn.ReLU, (), seed)
+
+
+def ae_chunk(c, rows=BATCH // CHUNKS):
+    """Chunk c of the synthetic batch: U[0,1) inputs, which double as the targets."""
+    g = torch.Generator().manual_seed(1000 + c)
+    return torch.rand(rows, AE_WIDTHS[0], generator=g)
+
+
+def mlp_data(seed=1, n=MLP_BATCH):
     g = torch.Generator().manual_seed(seed)
-    return torch.rand(n, WIDTHS[0], generator=g), torch.randint(0, WIDTHS[-1], (n,), generator=g)
+    return torch.rand(n, MLP_WIDTHS[0], generator=g), torch.randint(0, MLP_WIDTHS[-1], (n,), generator=g)
 
 
-def flops_per_product(n=BATCH):
+def flops_per_product(widths, n):
     """F_Gv = 2N(4S - 2 m1): contractions only."""
-    m = [WIDTHS[i] * WIDTHS[i + 1] for i in range(len(WIDTHS) - 1)]
+    m = [widths[i] * widths[i + 1] for i in range(len(widths) - 1)]
     return 2.0 * n * (4 * sum(m) - 2 * m[0])
+
+
+def config(n_gpus, params):
+    """Identical in both arms (the driver compares it)."""
+    return dict(workload=WORKLOAD, batch=BATCH, chunks=CHUNKS, params=params, cg_iters_per_step=K_CG, damping=DAMPING,
+                l2="flushed between steps (256 MiB write)",
+                parallelism=f"dp{n_gpus}: the 8 chunks dealt round-robin to the ranks, one all-reduce of the P-vector per CG iteration")
 
 
 def peaks():
@@ -67,7 +95,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -115,44 +143,49 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (reference cg.py + _Gv through the BackPACK recipe)
 # ------------------------------------------------------------------------------------------------------
-def cpu_solve_rate(solves, k_cg, threads=None):
+CPU_SAMPLE_ROWS = 1500  # bounded sample: 1/40 of the batch, same net, same 50 iterations per solve
+
+
+def cpu_solve_rate(solves, rows=CPU_SAMPLE_ROWS):
+    """Full-batch-equivalent products/s of the reference path on this host: K_CG-iteration solves on `rows` samples of
+    the workload; the cost of the reference's chunk loop is linear in the rows (optimizer.py:658-684), so the rate is
+    scaled by rows / BATCH."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import hf_oracle as O
 
-    if threads:
-        torch.set_num_threads(threads)
-    model = build_mlp(0)
-    loss_fn = torch.nn.CrossEntropyLoss()
-    x, t = synth(1)
+    torch.set_num_threads(os.cpu_count() or 1)  # all host threads, whatever OMP_NUM_THREADS the launcher exported
+    model = build_ae(0)
+    loss_fn = torch.nn.BCEWithLogitsLoss()
+    x = ae_chunk(0, rows)
     params = list(model.parameters())
     out = model(x)
-    loss = loss_fn(out, t)
+    loss = loss_fn(out, x)
     grad = O.flatten(torch.autograd.grad(loss, params, create_graph=True)).detach()
     M = O.diag_precond(torch.rand_like(grad) * 1e-3, DAMPING)  # same kind of operator; values do not affect cost
     A = lambda v: O.Gv(loss, out, params, v) + DAMPING * v  # noqa: E731
     O.pcg(A, -grad, M=M, max_iter=2, tol=0.0)  # warm-up
     t0 = time.perf_counter()
     for _ in range(solves):
-        O.pcg(A, -grad, M=M, max_iter=k_cg, tol=0.0)
+        O.pcg(A, -grad, M=M, max_iter=K_CG, tol=0.0)
     dt = time.perf_counter() - t0
     # the reference's cg spends K+1 products for K iterations (cg.py:188)
-    return solves * k_cg / dt, dt, torch.get_num_threads()
+    return solves * K_CG * (rows / BATCH) / dt, dt, torch.get_num_threads()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    k_cg = 5  # bounded sample: 5 CG iterations per step instead of 50, identical per-iteration work
-    cpu_solve_rate(max(1, args.warmup), k_cg)
-    rate, dt, threads = cpu_solve_rate(args.steps, k_cg)
+    params = sum(p.numel() for p in build_ae(0).parameters())
+    cpu_solve_rate(max(1, min(args.warmup, 2)))
+    rate, dt, threads = cpu_solve_rate(args.steps)
     line = dict(metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="mlp_784-512-512-10_relu_ce_batch4096_ggn_fisher_pcg", cg_iters_per_step=k_cg,
-                            damping=DAMPING, note="oracle port of reference cg.py + _Gv (BackPACK autograd recipe) on host cores"),
+                ms_per_step=1e3 * dt / args.steps / (CPU_SAMPLE_ROWS / BATCH), higher_is_better=True, scaling="strong",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=config(args.gpus, params),
                 cpu_baseline=dict(value=rate, unit=UNIT, cores=threads, kind="port",
-                                  sample=f"{args.steps} solves x {k_cg} CG iterations, batch {BATCH}"),
+                                  sample=f"{args.steps} solves x {K_CG} CG iterations on {CPU_SAMPLE_ROWS} of the {BATCH} samples "
+                                         f"({dt:.1f} s), rate scaled by {CPU_SAMPLE_ROWS}/{BATCH}; oracle port of reference cg.py + _Gv "
+                                         "(BackPACK autograd recipe)"),
                 e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -163,7 +196,7 @@ def run_reference(args):
 def run_native(args):
     import torch.distributed as dist
 
-    from pytorchhessianfree_b200 import DiagonalPreconditioner, _lib, pcg_device
+    from pytorchhessianfree_b200 import DiagonalPreconditioner, HessianFree, _lib, pcg_device
     from pytorchhessianfree_b200.lowering import lower_module
     from pytorchhessianfree_b200.native import NativeNet
     from pytorchhessianfree_b200.problem import NativeProblem
@@ -180,20 +213,20 @@ def run_native(args):
     lib = _lib.load()
     engine = args.engine
 
-    model = build_mlp(0).to(dev)
-    loss_fn = torch.nn.CrossEntropyLoss()
+    model = build_ae(0).to(dev)
+    loss_fn = torch.nn.BCEWithLogitsLoss()
     params = list(model.parameters())
     prog = lower_module(model, loss_fn, params)
     theta = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
     P = theta.numel()
     net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine)
-    x_host, t_host = synth(1 + rank)
-    x_host, t_host = x_host.pin_memory(), t_host.pin_memory()
-    x, t = x_host.to(dev), t_host.to(dev)
+    mine = [c for c in range(CHUNKS) if c % world == rank]
+    host = [ae_chunk(c).pin_memory() for c in mine]
+    resident = [h.to(dev) for h in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def setup(xd, td):
-        prob = NativeProblem(net, theta, "ggn", [(xd, td)], group=group)
+    def setup(chunks, grp):
+        prob = NativeProblem(net, theta, "ggn", [(x, x) for x in chunks], group=grp)
         prob.linearize()
         g = prob.gradient()
         M = DiagonalPreconditioner(prob.fisher_diag(), DAMPING)
@@ -208,8 +241,14 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-resident arm: inputs in HBM, linearisation done, time the solves -------------------
-    prob, g, M = setup(x, t)
+    prob, g, M = setup(resident, group)
     for _ in range(args.warmup):
         solve(prob, g, M)
     barrier()
@@ -226,30 +265,39 @@ def run_native(args):
             barrier()
             times.append(e0.elapsed_time(e1))
         launches = lib.hf_debug_launch_count() - n0
-        # nvidia-smi reports every ~100 ms and a 10-step timed region lasts ~0.1 s: keep the identical load running
-        # (untimed, same collectives on every rank) until the sampler has seen it
-        for _ in range(12):
-            for _ in range(4):
-                solve(prob, g, M)
-            torch.cuda.synchronize()
     assert why == "Number of iterations" and len(xs) == K_CG + 1, f"fixed-K solve stopped early: {why}, {len(xs) - 1} iterations"
-    total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
+    total_ms = reduce_max(sum(times))
+    value = args.steps * K_CG / (total_ms * 1e-3)
+    x_final = xs[-1].clone()
+
+    # ---- data-parallel correctness on the hardware: replicas bit-identical, and equal to the unsharded solve ----
+    checks = None
     if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    value = args.steps * K_CG * world / (total_ms * 1e-3)
+        lo, hi = x_final.clone(), x_final.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        identical = bool(torch.equal(lo, hi))
+        # every rank repeats the solve on all 8 chunks by itself (no collective) and compares
+        full = [ae_chunk(c).to(dev) for c in range(CHUNKS)]
+        p1, g1, M1 = setup(full, None)
+        x1 = solve(p1, g1, M1)[0][-1]
+        err = float(((x_final.double() - x1.double()).norm() / x1.double().norm()).item())
+        del p1, full
+        assert identical, "data-parallel replicas diverged: final CG iterates differ between ranks"
+        assert err < 1e-3, f"sharded solve differs from the single-GPU solve: rel L2 {err:.2e}"
+        checks = dict(replicas_bit_identical=identical, rel_l2_vs_unsharded=err)
 
     # ---- end-to-end arm: host buffers in, result out, everything inside the timed region -----------
     def e2e_step():
-        xd, td = x_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True)
-        pr, gg, MM = setup(xd, td)
+        chunks = [h.to(dev, non_blocking=True) for h in host]
+        pr, gg, MM = setup(chunks, group)
         xs_, _, _ = solve(pr, gg, MM)
         return xs_[-1].cpu()  # the Newton step (P floats) read back
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
     barrier()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, args.steps // 4)
     e2e_ms = 0.0
     for _ in range(e2e_steps):
         flush.fill_(1)
@@ -258,113 +306,207 @@ def run_native(args):
         e2e_step()
         torch.cuda.synchronize()
         e2e_ms += 1e3 * (time.perf_counter() - t0)
-    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_steps * K_CG * world / (float(e2e_t.item()) * 1e-3)
+    e2e_value = e2e_steps * K_CG / (reduce_max(e2e_ms) * 1e-3)
 
-    # ---- per-kernel rooflines, measured live (rank 0, kernels alone on the device) ------------------
+    # ---- the same through the optimizer's public API: get_preconditioner + acc_step on host tensors ----
+    def api_steps(mdl, lfn, datalist, first, n_steps, grp):
+        import warnings
+
+        opt = HessianFree(mdl.parameters(), process_group=grp)
+        ms, iters = [], []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in range(n_steps + 1):
+                barrier()
+                t0 = time.perf_counter()
+                Mf = opt.get_preconditioner(mdl, lfn, first[0], first[1], "mean")
+                opt.acc_step(mdl, lfn, datalist, M_func=Mf)
+                torch.cuda.synchronize()
+                if i:  # the first step pays lazy initialisation
+                    ms.append(1e3 * (time.perf_counter() - t0))
+                    iters.append(opt.state["num_cg_iters"][-1])
+        t = reduce_max(sum(ms))
+        return dict(ms_per_step=t / n_steps, cg_iters=iters, value=sum(iters) / (t * 1e-3), unit=UNIT,
+                    what="HessianFree.get_preconditioner (first local chunk) + acc_step on pinned host chunks: H2D, linearise, "
+                         "gradient, Fisher, PCG with Martens' criterion, cg-backtracking, line search, parameter update")
+
+    api_model = build_ae(0).to(dev)
+    e2e_api = api_steps(api_model, loss_fn, [(h, h) for h in host], (host[0], host[0]), 3, group)
+
+    # ---- the one collective of the path, alone ----
+    ar = None
+    if world > 1:
+        buf = torch.randn(P, device=dev)
+        from pytorchhessianfree_b200.dist import all_reduce_sum
+        for _ in range(5):
+            all_reduce_sum(buf, group)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            all_reduce_sum(buf, group)
+        e1.record()
+        barrier()
+        us = reduce_max(e0.elapsed_time(e1)) * 1e3 / 50
+        ar = dict(bytes=4 * P, us=us, bus_gbs=2.0 * (world - 1) / world * 4 * P / (us * 1e-6) / 1e9,
+                  note="NCCL all-reduce of the FP32 P-vector on the launching stream, back to back; reference 725 GB/s bus at 1 GiB")
+
+    # ---- per-kernel rooflines and the round-1 workload, measured live (rank 0, kernels alone on the device) ----
     pk = peaks()
     roof, extra = None, {}
     if rank == 0:
         # rank-local problem: the per-kernel timings must not issue collectives the other ranks do not join
-        local_prob = NativeProblem(net, theta, "ggn", [(x, t)], group=None)
+        local_prob = NativeProblem(net, theta, "ggn", [(resident[0], resident[0])], group=None)
         roof, extra = kernel_rooflines(lib, local_prob, theta, dev, pk, engine)
+        if world == 1:
+            extra["cfg2"] = cfg2_block(lib, dev, pk, engine, api_steps, barrier)
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            rate, dt, threads = cpu_solve_rate(2, 50)
+            rate, dt, threads = cpu_solve_rate(2)
             cpu = dict(value=rate, unit=UNIT, cores=threads, kind="port",
-                       sample=f"2 solves x 50 CG iterations of the same workload ({dt:.1f} s)")
+                       sample=f"2 solves x {K_CG} CG iterations on {CPU_SAMPLE_ROWS} of the {BATCH} samples ({dt:.1f} s), rate scaled "
+                              f"by {CPU_SAMPLE_ROWS}/{BATCH}")
+        cfg = config(world, P)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32", data="synthetic",
-                    config=dict(workload="mlp_784-512-512-10_relu_ce_batch4096_ggn_fisher_pcg", batch_per_gpu=BATCH,
-                                params=P, cg_iters_per_step=K_CG, damping=DAMPING, engine=engine,
-                                l2="flushed between steps (256 MiB write)",
-                                parallelism=f"dp{world}: batch sharded, all-reduce of the P-vector per CG iteration"),
+                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f32", data="synthetic", config=cfg, engine=engine,
                     clocks=clk.summary(), gpu_launches=int(launches),
-                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(x_host.numel() * 4 + t_host.numel() * 8),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(sum(h.numel() for h in host) * 4),
                              d2h_bytes_per_step=int(P * 4),
-                             what="H2D inputs + forward + gradient + Fisher diagonal + 50-iteration PCG + D2H step"),
-                    roofline=roof, cpu_baseline=cpu, **extra)
+                             what="H2D of the rank's chunks + forward + gradient + Fisher diagonal + 50-iteration PCG + D2H step"),
+                    e2e_api=e2e_api, roofline=roof, cpu_baseline=cpu, allreduce=ar, dp_checks=checks, **extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def kernel_rooflines(lib, prob, theta, dev, pk, engine):
-    """Time (a) one GGN-vector product and its dominant contraction, (b) the fused CG vector update, each alone
-    on the device with CUDA events, L2 flushed between launches."""
-    from pytorchhessianfree_b200.cg import _Solver
-    from pytorchhessianfree_b200._lib import PCG_FUSED
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def timed(fn, reps=10):
-        fn()
+def _timed(fn, flush, reps=10):
+    """Median CUDA-event time (ms) of fn alone on the device, L2 flushed before every launch."""
+    fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        flush.fill_(1)
         torch.cuda.synchronize()
-        ms = []
-        for _ in range(reps):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda._sleep(400_000)  # ~0.2 ms of device spin: the host enqueues e0/fn/e1 behind it, so the
-            e0.record()                 # interval holds device time only, not Python launch latency
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ms.append(e0.elapsed_time(e1))
-        ms.sort()
-        return ms[len(ms) // 2]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(400_000)  # ~0.2 ms of device spin: the host enqueues e0/fn/e1 behind it, so the
+        e0.record()                 # interval holds device time only, not Python launch latency
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2]
 
-    prob.linearize()
-    v, out = torch.randn_like(theta), torch.empty_like(theta)
-    t_mv = timed(lambda: prob.matvec(v, out))
-    f_mv = flops_per_product()
-    # dominant kernel: the tensor-tile contraction.  Timed on the shape that heads the launch list of a product, the
-    # layer-1 R-op forward  Rz1[4096,512] = a0[4096,784] V1[512,784]^T  (128 CTAs = one wave), through the same C entry
-    # point the products use.
+
+def contraction_roofline(lib, dev, pk, engine, M, N, K, what, flush):
+    """One tensor-tile contraction C[M,N] = A[M,K] B[N,K]^T through the C entry point the products use, timed alone.
+    On the tensor engine the pair kernel reads pre-split operand images, built once (engine 2) and then reused
+    (engine 3), exactly as a solve reuses the images of its linearisation."""
     from pytorchhessianfree_b200._lib import Operand
-    a0 = torch.randn(BATCH, 784, device=dev)
-    v1 = torch.randn(512, 784, device=dev)
-    c = torch.empty(BATCH, 512, device=dev)
-    A = (Operand * 1)(Operand(a0.data_ptr(), 784, 1))
-    B = (Operand * 1)(Operand(v1.data_ptr(), 784, 1))
-    eng = 1 if engine == "tc" else 0
+    a = torch.randn(M, K, device=dev)
+    b = torch.randn(N, K, device=dev)
+    c = torch.empty(M, N, device=dev)
+    A = (Operand * 1)(Operand(a.data_ptr(), K, 1))
+    B = (Operand * 1)(Operand(b.data_ptr(), K, 1))
     stream = torch.cuda.current_stream().cuda_stream
+    kernel = "gemm_simt_kernel"
+    eng, ws_ptr, ws_bytes = 0, None, 0
+    if engine == "tc":
+        ws_bytes = lib.hf_contract_workspace_bytes(M, N, K, 1)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        pair = os.environ.get("HF_TC2", "1") != "0" and M * N >= 74 * 256 * 256 * 0.75
+        if pair and lib.hf_contract(2, M, N, K, 1, A, B, c.data_ptr(), N, ws_ptr, ws_bytes, stream) == 0:
+            eng, kernel = 3, "gemm_tc2_kernel (256x256 CTA-pair tiles, pre-split operand images)"
+        else:
+            eng, kernel = 1, "gemm_tc_kernel (128x128 tiles, in-kernel splitter)"
 
-    def dom():
-        rc = lib.hf_contract(eng, BATCH, 512, 784, 1, A, B, c.data_ptr(), 512, None, 0, stream)
+    def run():
+        rc = lib.hf_contract(eng, M, N, K, 1, A, B, c.data_ptr(), N, ws_ptr, ws_bytes, stream)
         assert rc == 0, lib.hf_last_error_string()
-    t_dom = timed(dom)
-    f_dom = 2.0 * BATCH * 512 * 784
-    roof = dict(bound="tensor", achieved=f_dom / (t_dom * 1e-3) / 1e12, peak=pk["tf"], unit="TFLOP/s",
-                frac=f_dom / (t_dom * 1e-3) / 1e12 / pk["tf"],
-                traffic=17.9e6 if engine == "tc" else None,  # dram read+write per launch, ncu --set full (profiles/)
-                peak_source=pk["src"],
-                kernel=f"contraction 4096x512x784 (layer-1 R-op forward), engine={engine}",
-                us_per_launch=1e3 * t_dom,
+    t = _timed(run, flush)
+    f = 2.0 * M * N * K
+    tf = f / (t * 1e-3) / 1e12
+    return dict(bound="tensor", achieved=tf, peak=pk["tf"], unit="TFLOP/s", frac=tf / pk["tf"],
+                traffic=None,  # dram bytes per launch come from ncu --set full: profiles/r2_summary.md
+                peak_source=pk["src"], kernel=f"{kernel}: contraction {M}x{N}x{K} ({what})", us_per_launch=1e3 * t,
+                flops_per_launch=f,
                 note="split precision (TF32 main term + two BF16 correction terms = 4 bf16-MMA equivalents per product), "
                      "so the algorithmic ceiling is 1/4 of the bf16 peak")
-    # fused CG vector update at the Martens-autoencoder size (P = 2,837,314: larger than cfg2 so that the pass is
-    # bandwidth- rather than latency-bound) and at this workload's own P
+
+
+def kernel_rooflines(lib, prob, theta, dev, pk, engine):
+    """Time (a) one GGN-vector product on one 7 500-sample chunk and its dominant contraction, (b) the fused CG vector
+    update, each alone on the device with CUDA events, L2 flushed between launches."""
+    from pytorchhessianfree_b200._lib import PCG_FUSED
+    from pytorchhessianfree_b200.cg import _Solver
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    prob.linearize()
+    v, out = torch.randn_like(theta), torch.empty_like(theta)
+    n = prob.mvp_lins[0].n
+    t_mv = _timed(lambda: prob.matvec(v, out), flush)
+    f_mv = flops_per_product(AE_WIDTHS, n)
+    # dominant kernel: the layer-1 R-op forward  Rz1[7500,1000] = a0[7500,784] V1[1000,784]^T  heads the launch list of
+    # a product (profiles/r2_launches_cfg3.csv)
+    roof = contraction_roofline(lib, dev, pk, engine, n, AE_WIDTHS[1], AE_WIDTHS[0], "layer-1 R-op forward of one chunk", flush)
     upd = {}
-    for name, P in (("cfg2_P669706", theta.numel()), ("cfg3_P2837314", 2837314)):
+    for name, P in (("cfg3_P2837314", theta.numel()), ("cfg2_P669706", 669706)):
         b = torch.randn(P, device=dev)
         s = _Solver(b, 10 ** 6)
         minv = torch.rand(P, device=dev) + 0.5
         Bp = torch.randn(P, device=dev)
         s.init(None, None, minv, DAMPING, 0.0, None, False, False)
-        t_u = timed(lambda: s.iterate(PCG_FUSED, Bp=Bp, minv=minv, lam=DAMPING), reps=20)
+        t_u = _timed(lambda: s.iterate(PCG_FUSED, Bp=Bp, minv=minv, lam=DAMPING), flush, reps=20)
         gbs = 36.0 * P / (t_u * 1e-3) / 1e9
         upd[name] = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
                          us_per_launch=1e3 * t_u, bytes_per_launch=36 * P)
     extra = dict(roofline_cg_update=upd,
-                 matvec=dict(us_per_product=1e3 * t_mv, tflops_algorithmic=f_mv / (t_mv * 1e-3) / 1e12,
-                             flops_per_product=f_mv, frac_of_bf16_peak=f_mv / (t_mv * 1e-3) / 1e12 / pk["tf"]))
+                 matvec=dict(us_per_product=1e3 * t_mv, rows=n, tflops_algorithmic=f_mv / (t_mv * 1e-3) / 1e12,
+                             flops_per_product=f_mv, frac_of_bf16_peak=f_mv / (t_mv * 1e-3) / 1e12 / pk["tf"],
+                             what="one GGN-vector product on one 7 500-sample chunk (1/8 of a full-batch product)"))
     return roof, extra
+
+
+def cfg2_block(lib, dev, pk, engine, api_steps, barrier):
+    """BASELINE.json configs[1], the round-1 bench workload, for continuity: MLP 784-512-512-10 ReLU, CE, batch 4096."""
+    from pytorchhessianfree_b200 import DiagonalPreconditioner, pcg_device
+    from pytorchhessianfree_b200.lowering import lower_module
+    from pytorchhessianfree_b200.native import NativeNet
+    from pytorchhessianfree_b200.problem import NativeProblem
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    model = build_mlp(0).to(dev)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    params = list(model.parameters())
+    prog = lower_module(model, loss_fn, params)
+    theta = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+    net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine)
+    xh, th = mlp_data()
+    x, t = xh.to(dev), th.to(dev)
+    prob = NativeProblem(net, theta, "ggn", [(x, t)])
+    prob.linearize()
+    g = prob.gradient()
+    M = DiagonalPreconditioner(prob.fisher_diag(), DAMPING)
+
+    def solve():
+        return pcg_device(prob.matvec, -g, minv=M.minv, damping=DAMPING, max_iter=K_CG, tol=0.0, martens_conv_crit=False,
+                          store_x_at_iters=None, poll=K_CG)
+    t_solve = _timed(solve, flush, reps=10)
+    v, out = torch.randn_like(theta), torch.empty_like(theta)
+    t_mv = _timed(lambda: prob.matvec(v, out), flush)
+    f_mv = flops_per_product(MLP_WIDTHS, MLP_BATCH)
+    roof = contraction_roofline(lib, dev, pk, engine, MLP_BATCH, 512, 784, "layer-1 R-op forward", flush)
+    api = api_steps(build_mlp(0).to(dev), loss_fn, [(xh.pin_memory(), th.pin_memory())], (xh, th), 5, None)
+    return dict(workload="mlp_784-512-512-10_relu_ce_batch4096_ggn_fisher_pcg", params=theta.numel(),
+                value=K_CG / (t_solve * 1e-3), unit=UNIT, ms_per_step=t_solve,
+                matvec=dict(us_per_product=1e3 * t_mv, tflops_algorithmic=f_mv / (t_mv * 1e-3) / 1e12),
+                roofline=roof, e2e_api=api)
 
 
 def main():

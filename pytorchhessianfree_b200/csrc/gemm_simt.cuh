@@ -18,7 +18,7 @@ namespace hf {
 enum Epilogue {
   EPI_STORE = 0,      // C = alpha*acc (+bias)                      (partials, plain products)
   EPI_BIAS_ACT = 1,   // C = act(acc + bias)                        (forward pass)
-  EPI_BIAS_DACT = 2,  // C = (acc + bias) * act'(aux); C2 = acc+bias (R-op forward)
+  EPI_BIAS_DACT = 2,  // C = alpha * (acc + bias) * act'(aux); C2 = acc+bias (R-op forward)
   EPI_DACT = 3,       // C = acc * act'(aux); C2 = acc              (backward data)
   EPI_DACT_H = 4      // C = acc * act'(aux) + ga * act''(aux) * rz (Hessian backward data)
 };
@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_simt_kernel(GemmArgs g, int
           v += g.bias ? g.bias[n] : 0.f;
           if (g.C2) g.C2[(int64_t)m * g.ldc + n] = v;
           if (g.act != HF_ACT_NONE) v *= act_d1(g.act, g.aux[(int64_t)m * g.ldaux + n]);
+          v *= g.alpha;
         } break;
         case EPI_DACT: {
           if (g.C2) g.C2[(int64_t)m * g.ldc + n] = v;

@@ -49,6 +49,24 @@ struct Tc2Args {
   int a_mn[2], b_mn[2];  // 1 = operand is MN-contiguous in global memory (MN-major UMMA operand)
 };
 
+// Half of a B operand form set (64 rows at k0), multicast to the CTAs of `mask`: with two pairs per cluster the pairs
+// compute vertically adjacent tiles, share the B tile, and each CTA fetches a quarter of it for itself and for its
+// counterpart in the other pair -- 96 KB instead of 128 KB per pair and k-block come out of the L2, which is what
+// bounds the single-pair kernel on a full chip (profiles/r2_summary.md).
+__device__ __forceinline__ void load_half_multicast(uint32_t dst32, uint32_t dst_hi, uint32_t dst_lo, const CUtensorMap* maps, int mn_major,
+                                                    int row0, int k0, uint32_t bar, uint16_t mask) {
+  if (mn_major) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) tma_load_2d_pair_mc(dst32 + j * (BKT * 128), &maps[0], row0 + 32 * j, k0, bar, mask);
+    tma_load_2d_pair_mc(dst_hi, &maps[1], row0, k0, bar, mask);
+    tma_load_2d_pair_mc(dst_lo, &maps[2], row0, k0, bar, mask);
+  } else {
+    tma_load_2d_pair_mc(dst32, &maps[0], k0, row0, bar, mask);
+    tma_load_2d_pair_mc(dst_hi, &maps[1], k0, row0, bar, mask);
+    tma_load_2d_pair_mc(dst_lo, &maps[2], k0, row0, bar, mask);
+  }
+}
+
 // one operand form set of 128 rows at k0: FP32 tile + the two BF16 planes
 __device__ __forceinline__ void load_operand(uint32_t dst32, uint32_t dst_hi, uint32_t dst_lo, const CUtensorMap* maps, int mn_major,
                                              int row0, int k0, uint32_t bar) {
@@ -67,11 +85,15 @@ __device__ __forceinline__ void load_operand(uint32_t dst32, uint32_t dst_hi, ui
   }
 }
 
+// PAIRS = 1: cluster = one CTA pair.  PAIRS = 2: cluster = two pairs on vertically adjacent tiles sharing B by multicast.
+template <int PAIRS>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc2Args p) {
   const GemmArgs& g = p.g;
-  if (g.skip && *g.skip) return;  // uniform across the pair: solver already terminated
-  const uint32_t rank = cluster_ctarank();  // 0 = leader: issues the MMAs for both CTAs
+  if (g.skip && *g.skip) return;  // uniform across the cluster: solver already terminated
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;     // 0 = leader of its pair: issues the MMAs for both CTAs
+  const uint32_t pair_id = crank >> 1;  // which pair of the cluster
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(tiles + P2_STAGES * P2_STAGE_BYTES);
@@ -93,7 +115,7 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < P2_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], PAIRS);  // a stage is refilled by multicast from both pairs: both must have drained it
     }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -117,10 +139,17 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc
         // the leader arms its barrier for the bytes of both CTAs; the peer's complete_tx may arrive first (the phase
         // cannot complete before the leader's own arrival)
         if (rank == 0) mbar_expect_tx(&full[s], 2 * P2_STAGE_BYTES);
-        const uint32_t bar = map_to_cta(&full[s], 0);
+        const uint32_t bar = map_to_cta(&full[s], crank & ~1u);  // this pair's leader
         const uint32_t base = smem_u32(tiles + s * P2_STAGE_BYTES);
         load_operand(base + P2_A32, base + P2_AHI, base + P2_ALO, maps.m[pr][0], p.a_mn[pr], m0, k0, bar);
-        load_operand(base + P2_B32, base + P2_BHI, base + P2_BLO, maps.m[pr][1], p.b_mn[pr], nb0, k0, bar);
+        if (PAIRS == 1) {
+          load_operand(base + P2_B32, base + P2_BHI, base + P2_BLO, maps.m[pr][1], p.b_mn[pr], nb0, k0, bar);
+        } else {
+          // rows [nb0 + 64 pair_id, +64) of B for this CTA and for the CTA of the same pair rank in the other pair
+          const uint16_t mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
+          load_half_multicast(base + P2_B32 + pair_id * 8192, base + P2_BHI + pair_id * 4096, base + P2_BLO + pair_id * 4096,
+                              maps.m[pr][1], p.b_mn[pr], nb0 + 64 * (int)pair_id, k0, bar, mask);
+        }
       }
     }
   } else if (warp == 5) {
@@ -141,9 +170,9 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc
           umma2_bf16(tmem_base, corr_desc(base + P2_ALO, a_mn, ks), corr_desc(base + P2_BHI, b_mn, ks), idesc16, 1);
           umma2_bf16(tmem_base, corr_desc(base + P2_AHI, a_mn, ks), corr_desc(base + P2_BLO, b_mn, ks), idesc16, 1);
         }
-        umma2_commit(&empty[s]);  // frees the stage in both CTAs
+        umma2_commit(&empty[s], (uint16_t)((1u << (2 * PAIRS)) - 1));  // one arrival in every CTA of the cluster
       }
-      umma2_commit(acc_full);
+      umma2_commit(acc_full, (uint16_t)(3u << (2 * pair_id)));
     }
   } else {
     // ---------------- epilogue (both CTAs: 128 rows x 256 columns each) ----------------
@@ -267,7 +296,7 @@ int tc2_mode() {
   return mode;
 }
 
-static int operand_maps(CUtensorMap* out, const Operand& op, int MN, int K) {
+static int operand_maps(CUtensorMap* out, const Operand& op, int MN, int K, int box_rows) {
   const bool mn_major = op.s_k != 1;
   const CUtensorMap* m[3];
   if (mn_major) {
@@ -277,11 +306,11 @@ static int operand_maps(CUtensorMap* out, const Operand& op, int MN, int K) {
       m[1 + i] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op.img.hi + i * op.img.plane, (uint64_t)MN, (uint64_t)K,
                                    (uint64_t)op.img.ld * 2, 64, BKT, CU_TENSOR_MAP_SWIZZLE_128B);
   } else {
-    m[0] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, op.ptr, (uint64_t)K, (uint64_t)MN, (uint64_t)op.s_mn * 4, BKT, P2_ROWS,
-                             CU_TENSOR_MAP_SWIZZLE_128B);
+    m[0] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, op.ptr, (uint64_t)K, (uint64_t)MN, (uint64_t)op.s_mn * 4, BKT,
+                             (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
     for (int i = 0; i < 2; ++i)
       m[1 + i] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op.img.hi + i * op.img.plane, (uint64_t)K, (uint64_t)MN,
-                                   (uint64_t)op.img.ld * 2, BKT, P2_ROWS, CU_TENSOR_MAP_SWIZZLE_64B);
+                                   (uint64_t)op.img.ld * 2, BKT, (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_64B);
   }
   for (int i = 0; i < 3; ++i) {
     if (!m[i]) return HF_ERR_CUDA;
@@ -298,26 +327,36 @@ int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t stream) {
   if (g.split_k < 1) g.split_k = 1;
   if (g.split_k == 1) g.k_per_split = ((g.K + BKT - 1) / BKT) * BKT;
   HF_REQUIRE(g.k_per_split % BKT == 0, HF_ERR_INVALID, "tcgen05 engine: K split must be a multiple of %d", BKT);
+  // HF_TC2_MC=1: two pairs per cluster with B shared by multicast, when the tile rows pair up without much padding.
+  // Parity-green, but measured no faster on B200 (main loop 1.12 vs 0.97 us per k-block on a full chip, 132 instead of
+  // 148 SMs usable by 4-CTA clusters of this size): a multicast to <= 4 CTAs does not lower the L2 -> SM traffic that
+  // bounds the loop (profiles/r2_summary.md), so single-pair clusters are the default.
+  static const bool mc_allowed = getenv("HF_TC2_MC") && atoi(getenv("HF_TC2_MC")) != 0;
+  const int tiles_m = (g.M + P2_TILE - 1) / P2_TILE;
+  const int pairs = (mc_allowed && (tiles_m % 2 == 0 || tiles_m >= 9)) ? 2 : 1;
   Tc2Maps maps;
   for (int s = 0; s < 2; ++s) {
     const int src = s < g.n_pairs ? s : 0;
     p.a_mn[s] = g.A[src].s_k != 1, p.b_mn[s] = g.B[src].s_k != 1;
-    int rc = operand_maps(maps.m[s][0], g.A[src], g.M, g.K);
+    int rc = operand_maps(maps.m[s][0], g.A[src], g.M, g.K, P2_ROWS);
     if (rc) return rc;
-    rc = operand_maps(maps.m[s][1], g.B[src], g.N, g.K);
+    rc = operand_maps(maps.m[s][1], g.B[src], g.N, g.K, P2_ROWS / pairs);  // multicast: each CTA fetches 64 rows of B
     if (rc) return rc;
   }
   static bool seen[64] = {};
-  if (first_use_on_device(seen))
-    HF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
+  if (first_use_on_device(seen)) {
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * ((g.M + P2_TILE - 1) / P2_TILE), (g.N + P2_TILE - 1) / P2_TILE, g.split_k);
+  cfg.gridDim = dim3(2 * pairs * ((tiles_m + pairs - 1) / pairs), (g.N + P2_TILE - 1) / P2_TILE, g.split_k);
   cfg.blockDim = dim3(P2_THREADS), cfg.dynamicSmemBytes = P2_SMEM, cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = 2 * pairs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
   cfg.attrs = at, cfg.numAttrs = 1;
-  HF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, maps, p));
+  if (pairs == 2) HF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<2>, maps, p));
+  else HF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<1>, maps, p));
   note_launch();
   return HF_OK;
 }

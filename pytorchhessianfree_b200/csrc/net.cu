@@ -63,6 +63,7 @@ struct hf_lin {
   float* head_partB;          // [head.ctas][C]
   float* partial_main;        // second set for the first trainable layer, whose gradient runs on the caller's stream
   size_t partial_main_floats;
+  bool loss_fused;            // the last rop_forward already applied the (diagonal) loss Hessian in its epilogue
   int fwd_splits;             // > 0: the last rop_forward left split partials in partial_fwd
   const float* fwd_bias;
   std::vector<float*> cot;    // cot[l]: cotangent dloss/dz_l (or its R-derivative) of the sweep in flight
@@ -516,6 +517,7 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
     }
     float* dst = (hessian && l < nl - 1) ? lin->ra[l] : lin->buf[which];
     lin->fwd_splits = 0;
+    lin->loss_fused = false;
     if (l == nl - 1 && np > 0 && lin->partial_fwd && L.act == HF_ACT_NONE && net->engine == 1) {
       // Narrow output layer (10 classes): a 128x128 tensor tile per 128 rows would leave most SMs idle, so the
       // contraction is split over K instead and the loss-Hessian kernel sums the partial tiles (+ bias tangent).
@@ -551,6 +553,13 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
       g.epi = EPI_BIAS_DACT, g.act = L.act;
       g.bias = (L.has_bias && L.b_off >= 0) ? v + L.b_off : nullptr;
       g.aux = lin->a[l], g.ldaux = ld_out;
+      if (l == nl - 1 && L.act == HF_ACT_NONE && (net->loss == HF_LOSS_SIGMOID_BCE || net->loss == HF_LOSS_MSE)) {
+        // A diagonal loss Hessian rides in the epilogue of the last R-op contraction instead of a pass of its own:
+        // sigmoid-BCE  u = scale p(1-p) Rz  is "act' of a sigmoid" on the stored probabilities, MSE  u = 2 scale Rz.
+        g.alpha = loss_scale(net, lin->n_total) * (net->loss == HF_LOSS_MSE ? 2.f : 1.f);
+        if (net->loss == HF_LOSS_SIGMOID_BCE) g.act = HF_ACT_SIGMOID, g.aux = lin->prob;
+        lin->loss_fused = true;
+      }
       g.C2 = (hessian && curved(L.act)) ? lin->rz[l] : nullptr;
       g.c_img = image_for(lin, dst, L.out);  // the next layer's R-op (or the transposed sweep) reads it as an operand
       g.skip = skip;
@@ -567,6 +576,7 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
 }
 
 static int apply_loss_hessian(hf_lin* lin, float* rz, const int32_t* skip, cudaStream_t stream) {
+  if (lin->loss_fused) return HF_OK;  // done in the epilogue of the last R-op contraction
   const hf_net* net = lin->net;
   HessArgs h;
   h.rz = rz, h.prob = lin->prob, h.out = lin->a.back();
@@ -963,7 +973,7 @@ int hf_lin_create(const hf_net_t* net, int64_t batch, int32_t flags, void* d_wor
   hf_lin* lin = new (std::nothrow) hf_lin();
   HF_REQUIRE(lin, HF_ERR_INVALID, "hf_lin_create: out of host memory");
   lin->net = net, lin->N = batch, lin->flags = flags, lin->x = nullptr, lin->n_total = batch;
-  lin->have_forward = lin->have_gradient = false;
+  lin->have_forward = lin->have_gradient = false, lin->loss_fused = false;
   carve(net, batch, flags, static_cast<char*>(d_workspace), lin);
   lin->side = nullptr, lin->join = nullptr, lin->pending_cur = nullptr, lin->pending_cols = 0;
   if (!(flags & HF_LIN_LOSS_ONLY) && !getenv("HF_SINGLE_STREAM")) {

@@ -49,6 +49,16 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same box delivered to the same shared-memory offset of every CTA in `cta_mask` (one L2 read feeds them all); the
+// bytes are counted, per destination CTA, on the barrier that stands in the same self/peer relation to it as
+// `bar_cluster` does to the issuing CTA -- with bar_cluster = the issuer's pair leader: on every destination's leader
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -137,10 +147,11 @@ __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// completion of all prior MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+// completion of all prior MMAs of the pair -> one arrival on the barrier at this offset in every CTA of `cta_mask`
+// (default: the two CTAs of a cluster that is one pair)
+__device__ __forceinline__ void umma2_commit(uint64_t* bar, uint16_t cta_mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
+               "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -313,6 +324,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t stage,
         if (NEED_AUX)
 #pragma unroll
           for (int e = 0; e < 4; ++e) x[j][e] *= d1<ACT>(au[j][e]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[j][e] *= alpha;  // 1, or the scale of a fused diagonal loss Hessian
       } else if (EPI == EPI_DACT) {
         if (C2) st4<VEC>(C2 + m * ldc, cnt, x[j]);
         if (NEED_AUX)
