@@ -242,6 +242,39 @@ def ef_diag(model, loss_fn, inputs, targets, reduction: str) -> torch.Tensor:
     return acc / inputs.shape[0] if reduction == "mean" else acc
 
 
+def ef_diag_layerwise(model, loss_fn, inputs, targets, reduction: str) -> torch.Tensor:
+    """The same diagonal the way BackPACK's ``SumGradSquared`` forms it for ``nn.Linear`` (what
+    ``diag_EF_backpack`` reads, preconditioners.py:43-58): with ``d = d loss / d z_l`` (rows are per-sample
+    because the samples are independent) the per-sample gradients are ``d[n]^T a[n]`` and ``d[n]``, so
+    ``sum_n g_n^2 = (d^2)^T (a^2)`` for the weight and ``sum_n d^2`` for the bias; "mean" multiplies by N
+    because the loss already scaled every per-sample gradient by 1/N (preconditioners.py:56-58).  One
+    backward pass instead of N: usable as the oracle at benchmark batch sizes.  Pinned against the
+    per-sample loop ``ef_diag`` in tests/test_oracle_golden.py."""
+    if reduction not in ("sum", "mean"):
+        raise ValueError(f"reduction {reduction} is not supported.")
+    linears = [m for m in model.modules() if isinstance(m, torch.nn.Linear) and any(p.requires_grad for p in m.parameters())]
+    acts_in, outs = {}, {}
+    def remember(mod, args, out):  # returns None: the output is not replaced
+        acts_in[mod], outs[mod] = args[0].detach(), out
+
+    hooks = [m.register_forward_hook(remember) for m in linears]
+    try:
+        loss = loss_fn(model(inputs), targets)
+    finally:
+        for h in hooks:
+            h.remove()
+    deltas = torch.autograd.grad(loss, [outs[m] for m in linears])
+    by_param = {}
+    for m, d in zip(linears, deltas):
+        if m.weight.requires_grad:
+            by_param[m.weight] = (d * d).t() @ (acts_in[m] * acts_in[m])
+        if m.bias is not None and m.bias.requires_grad:
+            by_param[m.bias] = (d * d).sum(0)
+    params = [p for p in model.parameters() if p.requires_grad]
+    diag = flatten([by_param[p] for p in params])
+    return diag * inputs.shape[0] if reduction == "mean" else diag
+
+
 def diag_precond(diag: torch.Tensor, damping: float, exponent: float = 0.75) -> Callable:
     """x -> (diag + damping)^(-exponent) * x   (preconditioners.py:108-127)."""
     return lambda x: torch.mul((diag + damping) ** -exponent, x)

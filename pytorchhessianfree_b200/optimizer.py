@@ -364,8 +364,8 @@ class HessianFree(torch.optim.Optimizer):
         cached, self._prelinearized = getattr(self, "_prelinearized", None), None
         same_lists = grad_datalist is mvp_datalist and loss_datalist is mvp_datalist
         if (cached is not None and same_lists and self._group["curvature_opt"] == "ggn"
-                and cached[0] == self._problem_key(net, theta, mvp_data)):
-            _, problem, mvp_loss = cached  # linearised by get_preconditioner on the same data at the same parameters
+                and cached[0] == self._problem_key(net, theta, mvp_data) and torch.equal(cached[3], theta)):
+            _, problem, mvp_loss, _ = cached  # linearised by get_preconditioner on the same data at the same parameters
         else:
             problem = NativeProblem(
                 net, theta, self._group["curvature_opt"], mvp_data=mvp_data,
@@ -442,11 +442,15 @@ class HessianFree(torch.optim.Optimizer):
         diag = problem.fisher_diag()
         # The usual call order is get_preconditioner(x, t) followed by acc_step([(x, t)]) at the same parameters: keep
         # the linearisation so that acc_step does not repeat the forward pass (dropped as soon as anything differs).
-        self._prelinearized = (self._problem_key(net, theta, data), problem, loss)
+        # The key holds addresses and version counters; the parameter VALUES are compared too (a snapshot of theta,
+        # one device-side equality test in acc_step): `param.data` are views re-pointed into theta, so an in-place
+        # update of a parameter or `load_state_dict` changes theta without touching theta's own version counter.
+        self._prelinearized = (self._problem_key(net, theta, data), problem, loss, theta.clone())
         return DiagonalPreconditioner(diag, self._group["damping"], 0.75 if exponent is None else exponent)
 
-    @staticmethod
-    def _problem_key(net, theta, data):
-        """Identity of a linearisation: net, parameter buffer and its version, data buffers and their versions."""
-        return (net.signature(), theta.data_ptr(), theta._version,
+    def _problem_key(self, net, theta, data):
+        """Identity of a linearisation: net, parameter buffer, the version counters of the buffer and of every
+        parameter viewing it, data buffers and their versions (data edited through ``.data`` escapes the counters:
+        pass a new tensor, or call ``acc_step`` without a preceding ``get_preconditioner`` on that data)."""
+        return (net.signature(), theta.data_ptr(), theta._version, tuple(p._version for p in self._params_list),
                 tuple((x.data_ptr(), x._version, tuple(x.shape), t.data_ptr(), t._version, tuple(t.shape)) for x, t in data))

@@ -60,7 +60,8 @@ class NativeProblem:
     def gradient(self):
         """Flat gradient over the gradient chunks (``optimizer.py:725-765``); also primes the Hessian path."""
         assert self._linearized
-        g = torch.empty_like(self.theta)
+        # zeros, not empty: a rank whose shard is empty (fewer chunks than ranks) still joins the all-reduce
+        g = torch.empty_like(self.theta) if self.grad_lins else torch.zeros_like(self.theta)
         for i, lin in enumerate(self.grad_lins):
             lin.gradient(self.theta, g, accumulate=i > 0)
         if self.curvature_opt == "hessian" and self.grad_lins is not self.mvp_lins:
@@ -73,7 +74,7 @@ class NativeProblem:
     def fisher_diag(self):
         """Empirical-Fisher diagonal over the curvature chunks."""
         assert self._linearized
-        d = torch.empty_like(self.theta)
+        d = torch.empty_like(self.theta) if self.mvp_lins else torch.zeros_like(self.theta)
         for i, lin in enumerate(self.mvp_lins):
             lin.fisher(self.theta, d, accumulate=i > 0)
         _all_reduce(d, self.group)
@@ -99,6 +100,8 @@ class NativeProblem:
             upper.wait()
             first.wait()
             return
+        if not self.mvp_lins:
+            out.zero_()  # empty shard: contribute nothing to the sum over ranks
         for i, lin in enumerate(self.mvp_lins):
             if self.curvature_opt == "hessian":
                 lin.hessian(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)

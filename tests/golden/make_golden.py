@@ -115,6 +115,9 @@ def gold_matvec():
                     m2 = copy.deepcopy(model)
                     ef_b = diag_EF_backpack(m2, loss_fn, x, t, reduction)
                     same(ef_a, ef_b, "ef backpack-shim vs autograd", tol=1e-5)
+                    # independent pin of `_Gv` (all seeds, all nets): float64 forward-mode GGN, not the R-op recipe
+                    G64 = func_ggn64(model, loss_fn, x, t, v)
+                    same(G64, Gv.double(), "func64 GGN vs Gv", tol=2e-5)
                     rec = dict(net=name, seed=seed, reduction=reduction, n=n, x=x, t=t, v=v,
                                state={k: w.detach().clone() for k, w in model.state_dict().items()},
                                loss=loss.detach(), grad=grad, Gv=Gv, Hv=Hv, ef=ef_a)
@@ -133,6 +136,69 @@ def gold_matvec():
                     out.append(rec)
     torch.save(out, os.path.join(HERE, "matvec.pt"))
     print(f"matvec.pt: {len(out)} cases")
+
+
+# ---------------------------------------------------------------------------
+def func_ggn64(model, loss_fn, x, t, v):
+    """G v = J^T H_loss J v in float64 by forward-mode AD (torch.func.jvp), an analytic-free loss Hessian
+    (jvp of the loss gradient) and one vjp -- a derivation that shares nothing with the R-op recipe the oracle and
+    the BackPACK shim restate, so it pins `_Gv` independently of them."""
+    from torch.func import functional_call, grad, jvp, vjp
+
+    m64 = copy.deepcopy(model).double()
+    named = dict(m64.named_parameters())
+    train = [k for k, p in named.items() if p.requires_grad]
+    frozen = {k: p.detach() for k, p in named.items() if not p.requires_grad}
+    x64 = x.double()
+    t64 = t.double() if t.is_floating_point() else t
+    plist = tuple(named[k].detach() for k in train)
+    vlist = tuple(O.unflatten(v.double(), plist))
+
+    def net(*ps):
+        return functional_call(m64, {**frozen, **dict(zip(train, ps))}, (x64,))
+
+    out, Jv = jvp(net, plist, vlist)
+    _, HJv = jvp(grad(lambda z: loss_fn(z, t64)), (out,), (Jv,))
+    _, pull = vjp(net, *plist)
+    return O.flatten(pull(HJv))
+
+
+def gold_benchsize(stride=997):
+    """BASELINE.json configs[1] at batch 4096 and configs[2] at one 7 500-sample shard, the reference's seeds: gradient,
+    `_Gv`, `_Hv`, `diag_EF_backpack` from the unmodified reference.  Inputs and weights are re-created from seeds by
+    tests/helpers.py::benchsize_problem (their sums are stored to catch a drifting generator); of every P-vector only
+    each 997th entry and the L2 norm travel."""
+    from helpers import BENCH_CFGS, benchsize_problem
+
+    cases = []
+    for cfg in BENCH_CFGS:
+        for seed in SEEDS:
+            model, loss_fn, x, t, v = benchsize_problem(cfg, seed)
+            params = list(model.parameters())
+            outputs = model(x)
+            loss = loss_fn(outputs, t)
+            grad = O.flatten(torch.autograd.grad(loss, params, create_graph=True)).detach()
+            Gv = RefHF._Gv(loss, outputs, params, v)
+            Hv = RefHF._Hv(loss, params, v)
+            same(Gv, O.Gv(loss, outputs, params, v), "benchsize Gv")
+            same(Hv, O.Hv(loss, params, v), "benchsize Hv")
+            ef = diag_EF_backpack(copy.deepcopy(model), loss_fn, x, t, "mean")
+            same(ef, O.ef_diag_layerwise(model, loss_fn, x, t, "mean"), "benchsize ef", tol=1e-6)
+            G64 = func_ggn64(model, loss_fn, x, t, v)
+            rel = ((Gv.double() - G64).norm() / G64.norm()).item()
+            # (float32 reference vs float64 truth: up to ~2e-5 at these sizes -- a few ReLU units whose pre-activation sits
+            # within float32 rounding of zero take the other branch in float64; the stored value calibrates the GPU tolerance)
+            assert rel < 1e-4, f"reference _Gv vs independent float64 GGN: {rel:.2e}"
+            idx = torch.arange(0, v.numel(), stride)
+            w = torch.cat([p.detach().reshape(-1) for p in params])
+            cases.append(dict(cfg=cfg, seed=seed, n=x.shape[0], loss=loss.detach(), x_sum=float(x.double().sum()),
+                              v_sum=float(v.double().sum()), w_sum=float(w.double().sum()),
+                              grad=grad[idx].clone(), Gv=Gv[idx].clone(), Hv=Hv[idx].clone(), ef=ef[idx].clone(),
+                              Gv_func64=G64[idx].clone(), grad_norm=float(grad.double().norm()), Gv_norm=float(Gv.double().norm()),
+                              Hv_norm=float(Hv.double().norm()), ef_norm=float(ef.double().norm()), Gv_vs_func64=rel))
+            print(f"benchsize {cfg} seed {seed}: loss {loss.item():.6f}, |Gv| {cases[-1]['Gv_norm']:.4e}, ref-vs-func64 {rel:.1e}")
+    torch.save(dict(stride=stride, cases=cases), os.path.join(HERE, "benchsize.pt"))
+    print(f"benchsize.pt: {len(cases)} cases")
 
 
 # ---------------------------------------------------------------------------
@@ -247,6 +313,9 @@ def gold_selection():
 
 
 if __name__ == "__main__":
+    if "benchsize" in sys.argv:  # minutes of single-threaded autograd: minted on its own
+        gold_benchsize()
+        sys.exit(0)
     torch.set_num_threads(1)  # bit-stable reductions while minting
     gold_cg()
     gold_matvec()

@@ -75,3 +75,27 @@ def spd_system(dim, seed=0, dtype=torch.float32):
     A = R @ R.T + 1e-3 * torch.eye(dim)
     x = torch.rand(dim) - 0.5
     return A.to(dtype), (A @ x).to(dtype), x.to(dtype)
+
+
+# ---- BASELINE.json configs at benchmark size (tests/golden/benchsize.pt, tests/test_gpu_benchsize.py) ----
+BENCH_CFGS = {
+    # configs[1]: MLP 784-512-512-10 ReLU, CrossEntropy, batch 4096
+    "cfg2": dict(spec=dict(widths=[784, 512, 512, 10], act="relu", bias=[True] * 3, frozen=[], loss="ce"), n=4096),
+    # configs[2]: Martens autoencoder, one 7 500-sample shard (the per-GPU share of the 60 000 batch at 8 GPUs)
+    "cfg3": dict(spec=dict(widths=[784, 1000, 500, 250, 30, 250, 500, 1000, 784], act="sigmoid", bias=[True] * 8, frozen=[],
+                           loss="bce", linear_after=[3]), n=7500),
+}
+
+
+def benchsize_problem(cfg, seed):
+    """(model, loss_fn, x, t, v) of a benchmark-size parity case, re-created from the seed alone."""
+    c = BENCH_CFGS[cfg]
+    torch.manual_seed(seed)
+    model = build_model(c["spec"])
+    loss_fn = build_loss(c["spec"], "mean")
+    x, t = make_data(c["spec"], c["n"], 1000 + seed)
+    if c["spec"]["loss"] == "bce":
+        t = x.clone()  # the autoencoder reconstructs its inputs (SURVEY.md section 8d)
+    g = torch.Generator().manual_seed(2000 + seed)
+    v = torch.randn(sum(p.numel() for p in model.parameters() if p.requires_grad), generator=g)
+    return model, loss_fn, x, t, v

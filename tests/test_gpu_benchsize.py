@@ -1,0 +1,117 @@
+"""GPU: parity AT THE SIZES THAT ARE BENCHMARKED.  BASELINE.json configs[1] (MLP 784-512-512-10, batch 4096) and
+configs[2] (Martens autoencoder, one 7 500-sample shard = the per-GPU share at 8 GPUs), the reference's three seeds,
+default (tensor-core) engine: gradient, GGN product, Hessian product and empirical-Fisher diagonal
+
+  (a) against the CPU oracle run live on the same seeded inputs (one CPU product costs ~0.1-1 s at these sizes), and
+  (b) against tests/golden/benchsize.pt -- strided samples and norms of what the UNMODIFIED reference returned when
+      the fixture was minted (tests/golden/make_golden.py benchsize), so the GPU box needs no reference.
+
+Tolerance: north_star's rtol 1e-4 on matvec products, taken as max-abs error over max-abs value AND as relative L2
+error.  The float32 reference itself sits up to 2e-5 from the float64 truth here (fixture key Gv_vs_func64).
+Also pins the iteration at which Martens' criterion stops a well-conditioned (lambda = 1) solve of configs[1]."""
+import warnings
+
+import pytest
+import torch
+
+import hf_oracle as O
+from helpers import BENCH_CFGS, GOLDEN, benchsize_problem
+
+from pytorchhessianfree_b200 import DiagonalPreconditioner, pcg_device
+from pytorchhessianfree_b200.lowering import lower_module
+from pytorchhessianfree_b200.native import NativeNet
+from pytorchhessianfree_b200.problem import NativeProblem
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BS = torch.load(f"{GOLDEN}/benchsize.pt", weights_only=False)
+RTOL = 1e-4
+
+
+def errs(got, want):
+    got, want = got.double().cpu(), want.double()
+    return ((got - want).abs().max() / want.abs().max()).item(), ((got - want).norm() / want.norm()).item()
+
+
+def device_problem(model, loss_fn, x, t, curv, engine="tc"):
+    m = model.to(DEV)
+    params = list(m.parameters())
+    prog = lower_module(m, loss_fn, params)
+    theta = torch.cat([p.detach().reshape(-1) for p in params])
+    net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine)
+    prob = NativeProblem(net, theta, curv, [(x.to(DEV), t.to(DEV))])
+    return prob, theta
+
+
+@pytest.mark.parametrize("seed", [0, 1, 42])
+@pytest.mark.parametrize("cfg", list(BENCH_CFGS))
+def test_products_match_oracle_and_reference_samples(cfg, seed):
+    model, loss_fn, x, t, v = benchsize_problem(cfg, seed)
+    gold = next(c for c in BS["cases"] if c["cfg"] == cfg and c["seed"] == seed)
+    assert float(x.double().sum()) == pytest.approx(gold["x_sum"], rel=1e-12), "seeded inputs drifted from the fixture"
+    idx = torch.arange(0, v.numel(), BS["stride"])
+    # ---- CPU oracle, live ----
+    params = list(model.parameters())
+    out = model(x)
+    loss = loss_fn(out, t)
+    want = dict(grad=O.flatten(torch.autograd.grad(loss, params, retain_graph=True)),
+                Gv=O.Gv(loss, out, params, v), Hv=O.Hv(loss, params, v),
+                ef=O.ef_diag_layerwise(model, loss_fn, x, t, "mean"))
+    want_loss = float(loss)
+    # ---- device ----
+    import copy
+    got = {}
+    prob, theta = device_problem(copy.deepcopy(model), loss_fn, x, t, "ggn")
+    got_loss = float(prob.linearize().item())
+    got["grad"], got["Gv"], got["ef"] = prob.gradient(), prob.mvp(v.to(DEV)), prob.fisher_diag()
+    del prob
+    prob, _ = device_problem(copy.deepcopy(model), loss_fn, x, t, "hessian")
+    prob.linearize(), prob.gradient()
+    got["Hv"] = prob.mvp(v.to(DEV))
+    del prob
+    assert abs(got_loss - want_loss) <= 1e-5 * abs(want_loss)
+    assert abs(got_loss - float(gold["loss"])) <= 1e-5 * abs(want_loss)
+    report = {}
+    for k in ("grad", "Gv", "Hv", "ef"):
+        e_max, e_l2 = errs(got[k], want[k])
+        s_max, s_l2 = errs(got[k].cpu()[idx], gold[k])  # the reference's own numbers, sampled
+        n_rel = abs(float(got[k].double().norm()) - gold[f"{k}_norm"]) / gold[f"{k}_norm"]
+        report[k] = (e_max, e_l2, s_max, s_l2, n_rel)
+    msg = "; ".join(f"{k}: oracle max {a:.1e} l2 {b:.1e}, ref-sample max {c:.1e} l2 {d:.1e}, norm {e:.1e}" for k, (a, b, c, d, e) in report.items())
+    print(f"\n{cfg} seed {seed}: {msg}")
+    for k, (e_max, e_l2, s_max, s_l2, n_rel) in report.items():
+        assert e_max < RTOL and e_l2 < RTOL, f"{k} vs oracle: {msg}"
+        assert s_l2 < RTOL and n_rel < RTOL, f"{k} vs reference sample: {msg}"
+    # the independent float64 GGN (forward-mode AD, no R-op recipe) stored with the fixture
+    f_max, f_l2 = errs(got["Gv"].cpu()[idx], gold["Gv_func64"])
+    assert f_l2 < RTOL, f"Gv vs float64 torch.func GGN: max {f_max:.1e} l2 {f_l2:.1e}"
+
+
+@pytest.mark.parametrize("seed", [0, 1, 42])
+def test_martens_stop_iteration_is_pinned(seed):
+    """configs[1] at batch 4096, lambda = 1 (well conditioned), Fisher-diagonal preconditioner, Martens' criterion on:
+    the device solver must stop at exactly the iteration the reference's loop stops at, for the same reason."""
+    model, loss_fn, x, t, _ = benchsize_problem("cfg2", seed)
+    params = list(model.parameters())
+    out = model(x)
+    loss = loss_fn(out, t)
+    grad = O.flatten(torch.autograd.grad(loss, params, create_graph=True)).detach()
+    M = O.diag_precond(O.ef_diag_layerwise(model, loss_fn, x, t, "mean"), 1.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        xs, ms, why = O.pcg(lambda p: O.Gv(loss, out, params, p) + 1.0 * p, -grad, M=M, max_iter=250, martens_conv_crit=True,
+                            store_x_at_iters=None)
+    import copy
+    prob, theta = device_problem(copy.deepcopy(model), loss_fn, x, t, "ggn")
+    prob.linearize()
+    g = prob.gradient()
+    Md = DiagonalPreconditioner(prob.fisher_diag(), 1.0)
+    xs_d, ms_d, why_d = pcg_device(prob.matvec, -g, minv=Md.minv, damping=1.0, max_iter=250, martens_conv_crit=True,
+                                   store_x_at_iters=None)
+    assert why_d == why == O.REASON_MARTENS
+    assert len(xs_d) == len(xs), f"device stopped after {len(xs_d) - 1} iterations, the reference loop after {len(xs) - 1}"
+    e_max, e_l2 = errs(xs_d[-1], xs[-1])
+    assert e_l2 < 1e-3, f"final iterate: max {e_max:.1e} l2 {e_l2:.1e}"  # north_star: CG iterates within rtol 1e-3
+    m_ref = torch.stack(ms).double()
+    m_dev = torch.stack([m.cpu() for m in ms_d]).double()
+    assert torch.allclose(m_dev, m_ref, rtol=1e-3, atol=1e-7)

@@ -132,3 +132,46 @@ def test_user_supplied_mvp_on_quadratic(dim, seed):
         warnings.simplefilter("ignore")
         opt.step(forward, grad=(A @ p + b).detach(), mvp=lambda v: A @ v)
     assert torch.allclose(p.data, torch.linalg.solve(A, -b), atol=1e-3)
+
+
+def test_prelinearisation_is_dropped_when_parameters_change():
+    """get_preconditioner keeps its linearisation for the acc_step that follows.  If the parameters are updated in
+    between (in place, or by load_state_dict -- neither touches the flat buffer's own version counter), acc_step must
+    linearise again instead of reusing stale activations and ReLU masks."""
+    spec = SPECS["mlp_ce"]
+    loss_fn = build_loss(spec, "mean")
+    x, t = (a.to(DEV) for a in make_data(spec, 32, 9))
+
+    def run(mutate):
+        torch.manual_seed(4)
+        model = build_model(spec).to(DEV)
+        opt = HessianFree(model.parameters())
+        M = opt.get_preconditioner(model, loss_fn, x, t, "mean")
+        assert opt._prelinearized is not None
+        mutate(model)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            opt.acc_step(model, loss_fn, [(x, t)], M_func=M)
+        return opt.state["init_losses"][-1], float(loss_fn(model(x), t))
+
+    def scale(model):
+        with torch.no_grad():
+            for p in model.parameters():
+                p.mul_(1.5)
+
+    def reload(model):
+        sd = {k: 1.5 * w for k, w in model.state_dict().items()}
+        model.load_state_dict(sd)
+
+    torch.manual_seed(4)
+    fresh = build_model(spec).to(DEV)
+    with torch.no_grad():
+        for p in fresh.parameters():
+            p.mul_(1.5)
+    want = float(loss_fn(fresh(x), t))  # the loss acc_step must see as its starting point after the update
+    for mutate in (scale, reload):
+        init_loss, _ = run(mutate)
+        assert init_loss == pytest.approx(want, rel=1e-5), "acc_step reused the linearisation of the old parameters"
+    init_loss, _ = run(lambda m: None)  # unchanged parameters: the cache is valid and gives the same starting loss
+    torch.manual_seed(4)
+    assert init_loss == pytest.approx(float(loss_fn(build_model(spec).to(DEV)(x), t)), rel=1e-5)

@@ -134,3 +134,33 @@ def test_target_function_memo_and_linesearch_shortcuts():
     # a tensor modified in place is a new candidate
     cands[0].add_(3.0)
     assert f(cands[0]) == pytest.approx(4 * 4.0) and stub.passes[-1] == 1
+
+
+def test_repeated_module_instances_are_kept():
+    """A Sequential that applies ONE activation object after every Linear must lower to activation after every layer
+    (``children()`` de-duplicates instances; the walk uses ``_modules``)."""
+    act = nn.ReLU()
+    model = nn.Sequential(nn.Linear(4, 5), act, nn.Linear(5, 6), act, nn.Linear(6, 3))
+    prog = lower_module(model, nn.MSELoss(), list(model.parameters()))
+    assert [l.act for l in prog.layers] == ["relu", "relu", "none"]
+
+
+def test_shared_weights_are_refused():
+    """Two uses of one Linear would write the same slice of the flat vector twice in the transposed sweep."""
+    lin = nn.Linear(5, 5)
+    model = nn.Sequential(nn.Linear(4, 5), nn.Tanh(), lin, nn.Tanh(), lin)
+    with pytest.raises(NotImplementedError, match="more than one layer"):
+        lower_module(model, nn.MSELoss(), list(model.parameters()))
+    x = torch.rand(3, 4)
+    out = model(x)
+    with pytest.raises(NotImplementedError, match="more than one layer"):
+        lower_graph(nn.MSELoss()(out, torch.rand(3, 5)), out, list(model.parameters()))
+
+
+def test_untransposed_matmul_is_refused():
+    """``x @ W`` with a square W has the shapes of a Linear layer but the transposed meaning: refuse, do not guess."""
+    W = nn.Parameter(torch.rand(4, 4))
+    x = torch.rand(3, 4)
+    out = x @ W
+    with pytest.raises(NotImplementedError, match="weight.t"):
+        lower_graph(nn.MSELoss()(out, torch.rand(3, 4)), out, [W])

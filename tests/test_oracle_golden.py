@@ -57,6 +57,8 @@ def test_matvec_matches_reference(i):
     assert torch.allclose(O.Gv(loss, out, params, c["v"]), c["Gv"], rtol=1e-5, atol=1e-7)
     assert torch.allclose(O.Hv(loss, params, c["v"]), c["Hv"], rtol=1e-5, atol=1e-7)
     assert torch.allclose(O.ef_diag(model, loss_fn, c["x"], c["t"], c["reduction"]), c["ef"], rtol=1e-5, atol=1e-9)
+    # the one-pass (d^2)^T (a^2) form used as the oracle at benchmark batch sizes, against the reference's per-sample values
+    assert torch.allclose(O.ef_diag_layerwise(model, loss_fn, c["x"], c["t"], c["reduction"]), c["ef"], rtol=1e-4, atol=1e-9)
     if "Gv_dense64" in c:  # explicit J^T H J known answer (float64)
         assert torch.allclose(c["Gv"].double(), c["Gv_dense64"], rtol=1e-4, atol=1e-6)
         assert torch.allclose(c["Hv"].double(), c["Hv_dense64"], rtol=1e-4, atol=1e-6)
@@ -103,3 +105,35 @@ def test_selection_matches_reference():
             assert a == pytest.approx(c["alpha"]) and fa == pytest.approx(c["f"], rel=1e-5)
     p = SEL["precond"]
     assert torch.allclose(O.diag_precond(p["d"], p["damping"], p["exponent"])(p["v"]), p["out"])
+
+
+BS = torch.load(f"{GOLDEN}/benchsize.pt", weights_only=False)
+
+
+@pytest.mark.parametrize("i", range(len(BS["cases"])))
+def test_benchsize_fixture_inputs_regenerate(i):
+    """The benchmark-size fixtures store strided samples of the reference's results; inputs and weights are re-created
+    from seeds (a 4096 x 784 batch does not belong in git).  Check here, on CPU, that the seeded re-creation still lands
+    on the tensors the fixture was minted from; the GPU test relies on it."""
+    from helpers import benchsize_problem
+
+    c = BS["cases"][i]
+    model, loss_fn, x, t, v = benchsize_problem(c["cfg"], c["seed"])
+    assert float(x.double().sum()) == pytest.approx(c["x_sum"], rel=1e-12)
+    assert float(v.double().sum()) == pytest.approx(c["v_sum"], rel=1e-12)
+    w = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    assert float(w.double().sum()) == pytest.approx(c["w_sum"], rel=1e-12)
+
+
+def test_benchsize_oracle_reproduces_one_fixture():
+    """One benchmark-size case end to end on CPU (the MLP at batch 4096, seed 0): oracle vs the stored reference sample."""
+    from helpers import benchsize_problem
+
+    c = next(c for c in BS["cases"] if c["cfg"] == "cfg2" and c["seed"] == 0)
+    model, loss_fn, x, t, v = benchsize_problem("cfg2", 0)
+    params = list(model.parameters())
+    out = model(x)
+    loss = loss_fn(out, t)
+    idx = torch.arange(0, v.numel(), BS["stride"])
+    assert torch.allclose(O.Gv(loss, out, params, v)[idx], c["Gv"], rtol=1e-4, atol=1e-8)
+    assert torch.allclose(O.ef_diag_layerwise(model, loss_fn, x, t, "mean")[idx], c["ef"], rtol=1e-4, atol=1e-12)
