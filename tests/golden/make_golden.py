@@ -289,6 +289,35 @@ def gold_steps():
 
 
 # ---------------------------------------------------------------------------
+def gold_resume():
+    """Checkpoint fidelity: the UNMODIFIED reference optimizer takes 3 steps, its
+    ``state_dict()`` and the model travel in the fixture, and the reference's own next 3 steps are recorded.  The
+    drop-in optimizer must load that state_dict and continue on the same trajectory (tests/test_gpu_steps.py)."""
+    out = []
+    for name, curv in (("mlp_ce", "ggn"), ("ae_bce", "ggn"), ("tanh_mse", "hessian")):
+        spec = SPECS[name]
+        torch.manual_seed(5)
+        model = build_model(spec)
+        loss_fn = build_loss(spec, "mean")
+        opt = RefHF(model.parameters(), curvature_opt=curv, damping=0.7, cg_max_iter=30)
+        data = [make_data(spec, 24, 300 + s) for s in range(6)]
+        for x, t in data[:3]:
+            opt.step(lambda: (lambda o: (loss_fn(o, t), o))(model(x)))
+        blob = copy.deepcopy(opt.state_dict())
+        mid_state = {k: w.detach().clone() for k, w in model.state_dict().items()}
+        n_before = len(opt.state["init_losses"])
+        for x, t in data[3:]:
+            opt.step(lambda: (lambda o: (loss_fn(o, t), o))(model(x)))
+        out.append(dict(net=name, curv=curv, optimizer_state_dict=blob, model_state=mid_state, data=data[3:],
+                        init_losses=list(opt.state["init_losses"][n_before:]), dampings=list(opt.state["dampings"][n_before:]),
+                        num_cg_iters=list(opt.state["num_cg_iters"][n_before:]), cg_reasons=list(opt.state["cg_reasons"][n_before:]),
+                        final_state={k: w.detach().clone() for k, w in model.state_dict().items()}))
+        assert isinstance(blob["state"]["x0"], torch.Tensor) and blob["param_groups"][0]["damping"] == opt.state["dampings"][n_before]
+    torch.save(out, os.path.join(HERE, "resume.pt"))
+    print(f"resume.pt: {len(out)} checkpoints taken from the reference optimizer")
+
+
+# ---------------------------------------------------------------------------
 def gold_selection():
     toy = [2.0, 1.0, None, 2.7, 2.4, None, None, 7.3]  # reference tests/test_cg_backtracking.py:8
     b1, v1 = cg_backtracking(lambda s: s, toy)
@@ -316,8 +345,13 @@ if __name__ == "__main__":
     if "benchsize" in sys.argv:  # minutes of single-threaded autograd: minted on its own
         gold_benchsize()
         sys.exit(0)
+    if "resume" in sys.argv:
+        torch.set_num_threads(1)
+        gold_resume()
+        sys.exit(0)
     torch.set_num_threads(1)  # bit-stable reductions while minting
     gold_cg()
     gold_matvec()
     gold_steps()
+    gold_resume()
     gold_selection()

@@ -175,3 +175,76 @@ def test_prelinearisation_is_dropped_when_parameters_change():
     init_loss, _ = run(lambda m: None)  # unchanged parameters: the cache is valid and gives the same starting loss
     torch.manual_seed(4)
     assert init_loss == pytest.approx(float(loss_fn(build_model(spec).to(DEV)(x), t)), rel=1e-5)
+
+
+RESUME = torch.load(f"{GOLDEN}/resume.pt", weights_only=False)
+
+
+@pytest.mark.parametrize("i", range(len(RESUME)))
+def test_resume_from_a_reference_checkpoint(i):
+    """Load the ``state_dict()`` the UNMODIFIED reference optimizer produced after 3 steps (damping in
+    ``param_groups[0]``, warm start ``x0`` and the log lists under string keys, reference optimizer.py:104-110,
+    :183-192) into the drop-in optimizer and continue: the next 3 steps must follow the reference's own."""
+    c = RESUME[i]
+    spec = SPECS[c["net"]]
+    model = build_model(spec)
+    model.load_state_dict(c["model_state"])
+    model.to(DEV)
+    loss_fn = build_loss(spec, "mean")
+    opt = HessianFree(model.parameters(), curvature_opt=c["curv"])
+    opt.load_state_dict(copy.deepcopy(c["optimizer_state_dict"]))
+    assert opt._group["damping"] == c["dampings"][0] and opt._group["cg_max_iter"] == 30
+    opt.state["x0"] = opt.state["x0"].to(DEV)  # as a user moving a checkpoint between devices would
+    n0 = len(opt.state["init_losses"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for x, t in c["data"]:
+            x, t = x.to(DEV), t.to(DEV)
+            opt.step(lambda: (lambda o: (loss_fn(o, t), o))(model(x)))
+    got = opt.state["init_losses"][n0:]
+    assert len(got) == 3
+    if c["curv"] == "ggn":  # (indefinite-Hessian tanh runs are chaotic in the reference itself: first step only)
+        assert torch.allclose(torch.tensor(got), torch.tensor(c["init_losses"]), rtol=1e-3)
+        assert torch.allclose(torch.tensor(opt.state["dampings"][n0:]), torch.tensor(c["dampings"]), rtol=1e-6)
+        assert opt.state["cg_reasons"][n0:] == c["cg_reasons"]
+        for k, w in model.state_dict().items():
+            assert torch.allclose(w.cpu(), c["final_state"][k], rtol=1e-3, atol=1e-4)
+    else:
+        assert got[0] == pytest.approx(c["init_losses"][0], rel=1e-4)
+        assert opt.state["dampings"][n0] == pytest.approx(c["dampings"][0])
+
+
+@pytest.mark.parametrize("curv", ["ggn", "hessian"])
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+def test_acc_step_with_distinct_data_lists(curv, reduction):
+    """acc_step with three DIFFERENT chunk lists for the loss, the gradient and the curvature products (reference
+    optimizer.py:575-597), ragged chunk sizes, against the oracle's acc_step on the same lists."""
+    import hf_oracle as O
+
+    spec = SPECS["mlp_ce"]
+    torch.manual_seed(11)
+    ref_model = build_model(spec)
+    model = copy.deepcopy(ref_model).to(DEV)
+    loss_fn = build_loss(spec, reduction)
+    opt = HessianFree(model.parameters(), curvature_opt=curv, cg_max_iter=12)
+    orc = O.OracleHF(ref_model.parameters(), curvature_opt=curv, cg_max_iter=12)
+
+    def lists(step):
+        xl, tl = make_data(spec, 40, 50 + step)
+        xg, tg = make_data(spec, 23, 60 + step)
+        xm, tm = make_data(spec, 17, 70 + step)
+        return chunked(xl, tl, [13, 27]), chunked(xg, tg, [23]), chunked(xm, tm, [5, 4, 8])
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for step in range(3):
+            ll, gl, ml = lists(step)
+            dev = lambda dl: [(x.to(DEV), t.to(DEV)) for x, t in dl]  # noqa: E731
+            opt.acc_step(model, loss_fn, dev(ll), grad_datalist=dev(gl), mvp_datalist=dev(ml), reduction=reduction)
+            orc.acc_step(ref_model, loss_fn, ll, grad_datalist=gl, mvp_datalist=ml, reduction=reduction)
+            assert opt.state["init_losses"][-1] == pytest.approx(orc.log["init_losses"][-1], rel=1e-4)
+            if curv == "ggn":
+                for p, q in zip(model.parameters(), ref_model.parameters()):
+                    assert torch.allclose(p.data.cpu(), q.data, atol=1e-4)
+    if curv == "ggn":
+        assert opt.state["num_cg_iters"] == orc.log["num_cg_iters"]
