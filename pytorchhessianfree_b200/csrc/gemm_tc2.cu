@@ -201,7 +201,7 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc
 #pragma unroll
     for (int h = 0; h < 2; ++h)
       epilogue_dispatch<P2_LDS_ROW>(g, stage, h * 128 + lane * 4, m0 + warp * 32, n0 + h * 128 + lane * 4, cs[h]);
-    if (g.colpart) {
+    if (g.colpart && m0 < g.M) {  // (the grid is padded to whole pairs: a CTA entirely below the matrix owns no row of colpart)
       // 4 warps x 32 rows -> one row of column sums per CTA (= per 128-row block, like gemm_tc.cu), fixed order
       float* red = reinterpret_cast<float*>(tiles) + 4 * 32 * P2_LDS_ROW;
 #pragma unroll

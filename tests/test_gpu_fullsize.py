@@ -114,3 +114,32 @@ def test_public_api_trains_the_mlp_config(engine):
     if len(seen) == 2:
         for a, b in zip(seen["tc"], seen["simt"]):
             assert a == pytest.approx(b, rel=1e-3)
+
+
+@pytest.mark.parametrize("curv", ["ggn", "hessian"])
+def test_products_are_bitwise_repeatable(curv):
+    """The same product launched repeatedly, and two independently allocated linearisations of the same problem, return
+    the same bits: every reduction is fixed-order, nothing is atomically accumulated, and no kernel writes outside its
+    tile (a 7 500-row chunk has an odd number of 128-row blocks, so the CTA-pair grid is padded -- the padding CTA of
+    an early build scribbled over row 0 of a cotangent, which only this test caught)."""
+    torch.manual_seed(0)
+    model = build_model(AE).to(DEV)
+    loss_fn = build_loss(AE, "mean")
+    x = torch.rand(2 * 7500, 784, device=DEV)
+    params = list(model.parameters())
+    prog = lower_module(model, loss_fn, params)
+    theta = torch.cat([p.detach().reshape(-1) for p in params])
+    net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine="tc")
+    v = torch.randn_like(theta)
+
+    def fresh():
+        prob = NativeProblem(net, theta, curv, [(x[:7500], x[:7500]), (x[7500:], x[7500:])])
+        prob.linearize()
+        return prob, prob.gradient()
+
+    (p1, g1), (p2, g2) = fresh(), fresh()
+    assert torch.equal(g1, g2)
+    outs = [p1.mvp(v) for _ in range(4)] + [p2.mvp(v) for _ in range(2)]
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+    assert torch.equal(p1.fisher_diag(), p2.fisher_diag())
