@@ -30,6 +30,7 @@ struct SplitSegment {
   float* dst32;  // optional FP32 copy with pitch ld32 (multiple of 4)
   int64_t ld32;
   Image16 img;   // optional
+  int square;    // 1: every element is squared first (operands of the empirical-Fisher contraction)
 };
 constexpr int kMaxSplitSegments = 20;
 struct SplitTable {

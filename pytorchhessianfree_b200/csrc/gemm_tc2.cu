@@ -239,6 +239,10 @@ __global__ void __launch_bounds__(256) split_segments_kernel(SplitTable t) {
     } else {
       for (int e = 0; e < cnt; ++e) x[e] = src[e];
     }
+    if (s.square) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] *= x[e];
+    }
     if (s.dst32) *reinterpret_cast<float4*>(s.dst32 + r * s.ld32 + c) = make_float4(x[0], x[1], x[2], x[3]);  // pitch % 4 == 0
     if (s.img.hi) st4_image(s.img, r, c, 4, x);  // image pitch % 8 == 0: the padding columns get zeros
   }

@@ -38,6 +38,7 @@ struct hf_net {
   int max_width;
   int classes;
   int engine;  // 0 = SIMT everywhere, 1 = tcgen05 where the shape allows
+  bool has_relu;
 };
 
 struct hf_lin {
@@ -86,6 +87,10 @@ struct hf_lin {
   std::vector<ImgBuf> imgs;
   ImgBuf x_img;
   std::vector<ImgBuf> w_img, v_img;  // per layer; base filled in when the parameter / direction pointer is known
+  // Empirical-Fisher diagonal on the tensor engines: (d^2)^T (a^2) is an ordinary contraction of the SQUARED operands,
+  // which one split pass writes here (FP32 with a 16-byte pitch, + images when the linearisation keeps them).
+  float* sq[2];
+  ImgBuf sq_img[2];
   const float* pending_cur;   // phased sweep: cotangent of the first trainable layer, left by phase 0 for phase 1
   int pending_cols;
   cudaStream_t side;          // weight/bias gradients of layer l run here, concurrently with the data product that
@@ -417,8 +422,26 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
     GemmArgs g = blank_gemm();
     g.M = M, g.N = N, g.K = (int)lin->N, g.n_pairs = n_pairs;
     for (int s = 0; s < n_pairs; ++s) g.A[s] = A[s], g.B[s] = B[s];
-    g.square = square;
-    SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, square));
+    int gemm_square = square;  // (the bias slice below still needs `square` for its column sums)
+    if (square && lin->sq[0] && n_pairs == 1 && A[0].s_mn == 1 && B[0].s_mn == 1 && (int64_t)M * N * lin->N >= kTcMinWork) {
+      // Fisher diagonal as a tensor-core contraction: square the two operands once (one launch), contract as usual
+      SplitTable t;
+      t.count = 2, t.skip = skip;
+      Operand sqop[2];
+      for (int w = 0; w < 2; ++w) {
+        const Operand& src = w ? B[0] : A[0];
+        const int cols = w ? N : M;
+        const Image16 im = lin->sq_img[w].hi ? Image16{lin->sq_img[w].hi, lin->sq_img[w].plane, pad8(cols)} : Image16{nullptr, 0, 0};
+        t.seg[w] = SplitSegment{src.ptr, lin->N, cols, src.s_k, lin->sq[w], pad4(cols), im, 1};
+        sqop[w] = Operand{lin->sq[w], 1, pad4(cols), im};
+      }
+      int rcs = launch_split(t, stream);
+      if (rcs) return rcs;
+      g.A[0] = sqop[0], g.B[0] = sqop[1];
+      gemm_square = 0;
+    }
+    g.square = gemm_square;
+    SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, gemm_square));
     int pair_hint = 0;
     if (lin->net->engine == 1 && tc2_mode() != 0 && tc2_supported(g)) {
       // both engines can take it: compare the modelled times of their own best split
@@ -645,7 +668,8 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
   // The sweep is a chain of data products (cot[l] -> cot[l-1]) on the caller's stream; the parameter gradients of
   // layer l only need cot[l], so they run on the side stream while the chain moves on.  Every cotangent has its
   // own buffer, so there is no write-after-read hazard between the two streams.
-  const bool fork = lin->side != nullptr && phase != 1;
+  // (the Fisher sweep runs once per step and shares one pair of squared-operand buffers between its layers: no fork)
+  const bool fork = lin->side != nullptr && phase != 1 && mode != BACK_FISHER;
   cudaStream_t gstream = fork ? lin->side : stream;
   const float* cur = top;
   int cur_col_tiles = 0;  // > 0: the kernel that produced `cur` also left its column sums in colbuf[l]
@@ -751,7 +775,7 @@ int hf_net_create(const hf_layer_desc* layers, int32_t n_layers, int32_t loss, i
   hf_net* net = new (std::nothrow) hf_net();
   HF_REQUIRE(net, HF_ERR_INVALID, "hf_net_create: out of host memory");
   net->loss = loss, net->reduction = reduction, net->P = n_params;
-  net->first_trainable = -1, net->max_width = 0, net->engine = 0;
+  net->first_trainable = -1, net->max_width = 0, net->engine = 0, net->has_relu = false;
   for (int i = 0; i < n_layers; ++i) {
     const hf_layer_desc& d = layers[i];
     bool ok = d.in_features > 0 && d.out_features > 0 && d.act >= HF_ACT_NONE && d.act <= HF_ACT_TANH;
@@ -765,6 +789,7 @@ int hf_net_create(const hf_layer_desc* layers, int32_t n_layers, int32_t loss, i
     Layer l{d.in_features, d.out_features, d.act, d.has_bias, d.w_offset, d.has_bias ? d.b_offset : -1, d.d_w_frozen,
             d.d_b_frozen};
     if (net->first_trainable < 0 && (l.w_off >= 0 || l.b_off >= 0)) net->first_trainable = i;
+    if (l.act == HF_ACT_RELU) net->has_relu = true;
     net->max_width = std::max(net->max_width, std::max(l.in, pad4(l.out)));
     net->L.push_back(l);
   }
@@ -901,6 +926,13 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       float* ct = l < nl - 1 ? (float*)take(sizeof(float) * N * pad4(net->L[l].out)) : nullptr;
       if (lin) lin->colbuf[l] = cb, lin->cot[l] = ct;
     }
+  float* sq0 = nullptr;
+  float* sq1 = nullptr;
+  if (!loss_only && net->engine == 1) {
+    sq0 = (float*)take(sizeof(float) * N * pad4(net->max_width));
+    sq1 = (float*)take(sizeof(float) * N * pad4(net->max_width));
+  }
+  if (lin) lin->sq[0] = sq0, lin->sq[1] = sq1, lin->sq_img[0] = lin->sq_img[1] = {nullptr, nullptr, 0};
   // split-precision images: two BF16 planes per matrix, row pitch pad8(width)
   if (lin) lin->use_images = images, lin->imgs.clear(), lin->x_img = {nullptr, nullptr, 0},
            lin->w_img.assign(nl, {nullptr, nullptr, 0}), lin->v_img.assign(nl, {nullptr, nullptr, 0});
@@ -922,6 +954,10 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
     }
     const hf_lin::ImgBuf dl = take_img(dL, N, net->classes);
     if (lin) lin->imgs.push_back(dl);
+    for (int i = 0; i < 2; ++i) {
+      const hf_lin::ImgBuf b = take_img(i ? sq1 : sq0, N, net->max_width);
+      if (lin) lin->sq_img[i] = b;
+    }
     for (int l = net->first_trainable; l < nl; ++l) {
       const Layer& L = net->L[l];
       if (l < nl - 1) {
@@ -1020,7 +1056,10 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     // ~5e-6 error of the split-precision tensor tiles would flip a few dozen of the 4M masks of the MLP config (each flip moves a
     // gradient row by ~1/sqrt(N)).  Loss-only evaluations (line search, backtracking) have no masks to fix and
     // stay on the tensor-core tiles.
-    int rc = (lin->flags & HF_LIN_LOSS_ONLY) ? run_gemm(net, g, stream) : launch_gemm_simt(g, stream);
+    // Nets without ReLU have no masks to fix: their linearisation point tolerates the ~5e-6 of the tensor tiles, which
+    // only moves it as a slightly different parameter vector would.
+    const bool exact = !(lin->flags & HF_LIN_LOSS_ONLY) && net->has_relu;
+    int rc = exact ? launch_gemm_simt(g, stream) : run_gemm(net, g, stream);
     if (rc) return rc;
   }
   {
