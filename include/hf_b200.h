@@ -78,6 +78,10 @@ int hf_debug_pcg_trace(void* d_buf);
  * consecutive blocks of 1024 CTA records (d_buf >= launches * 1024 * 8 uint64), so gaps between kernels can be read
  * off too; NULL switches the trace off. */
 int hf_debug_tc_trace(void* d_buf);
+/* the same for the CTA-pair kernel on pre-split operands (gemm_tc2.cu), one block of 4096 CTA records that every launch
+ * overwrites: [cta][0] entry, [1] prologue done, [2] first stage landed, [3] accumulator complete, [4] first 128 columns
+ * staged, [5] first 128 columns stored, [6] all stored, [7] pair released (d_buf >= 4096 * 8 uint64) */
+int hf_debug_tc2_trace(void* d_buf);
 /* per-k-block pipeline trace of CTA (0,0,0) of the same kernel, first 64 k-blocks: [it][0] TMA issued, [1] raw tiles seen
  * by the splitters, [2] split done, [3] MMAs issued, [4] producer's slot wait done (d_buf >= 64 * 8 uint64) */
 int hf_debug_tc_trace_iters(void* d_buf);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "hf_debug_launch_count": (C.c_longlong, []),
     "hf_debug_pcg_trace": (C.c_int, [_vp]),
     "hf_debug_tc_trace": (C.c_int, [_vp]),
+    "hf_debug_tc2_trace": (C.c_int, [_vp]),
     "hf_debug_tc_trace_iters": (C.c_int, [_vp]),
     "hf_pcg_state_bytes": (_sz, [_i64]),
     "hf_pcg_m_iters_offset": (_sz, []),

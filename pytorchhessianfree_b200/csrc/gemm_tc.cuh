@@ -19,6 +19,7 @@ struct Tc2Choice {
   double us_pair, us_single;  // modelled time on the pair engine / on the 128x128 engine
 };
 Tc2Choice tc2_estimate(int M, int N, int K, int n_pairs, int splits);
+int set_tc2_trace(void* d_buf);  // per-CTA phase timestamps of the pair kernel (d_buf: 4096 x 8 uint64), NULL = off
 int tc2_mode();  // HF_TC2: 0 = never, 1 = where the model prefers it (default), 2 = wherever it is supported
 
 // img = split(src) (+ optional 16-byte-pitched FP32 copy) for several matrices in one launch

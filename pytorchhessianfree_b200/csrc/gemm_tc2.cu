@@ -35,11 +35,56 @@ namespace hf {
 constexpr int P2_ROWS = 128;                    // rows of A, and of B, one CTA stages
 constexpr int P2_TILE = 256;                    // pair tile: 256 x 256
 constexpr int P2_STAGES = 3;
-constexpr int P2_A32 = 0, P2_AHI = 16384, P2_ALO = 24576, P2_B32 = 32768, P2_BHI = 49152, P2_BLO = 57344;
-constexpr int P2_STAGE_BYTES = 65536;
-constexpr int P2_SMEM = P2_STAGES * P2_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int P2_THREADS = 192;
-constexpr int P2_LDS_ROW = P2_TILE + 4;         // staged accumulator rows: 4 warps x 32 rows x 260 floats = 130 KB
+constexpr int P2_LDS_ROW = 128 + 4;             // staged accumulator rows, 128 columns per pass: 4 warps x 32 rows x 132 floats = 66 KB
+
+// Two builds of the same kernel, by k-block width BK (floats of K per pipeline stage):
+//   BK = 32: 64 KB per stage, 193 KB per CTA, ONE CTA per SM (the default).  Three stages hide the L2 latency of a lone
+//            CTA: with L2-resident operands the main loop runs at the MMA floor (0.50-0.60 us per k-block,
+//            tools/tc2_slope.py).  Everything outside the loop is exposed: per 128x256 CTA tile ~3.3 us of prologue and
+//            pipeline fill and ~7.4 us of epilogue (tools/tc2_trace.py).
+//   BK = 16: 32 KB per stage, 97 KB per CTA, TWO CTAs per SM (two pairs per TPC, 2 x 256 TMEM columns); HF_TC2_BK=16.
+//            Parity-green; meant to run one pair's epilogue under the other pair's main loop, but co-resident pairs of one
+//            launch run in lockstep, so it measures the same as BK = 32.  Kept for the persistent variant that staggers them.
+template <int BK>
+struct P2Cfg {
+  static constexpr int OP32 = P2_ROWS * BK * 4;   // FP32 tile of one operand
+  static constexpr int OP16 = P2_ROWS * BK * 2;   // one BF16 plane
+  static constexpr int A32 = 0, AHI = OP32, ALO = OP32 + OP16, B32 = OP32 + 2 * OP16, BHI = B32 + OP32, BLO = BHI + OP16;
+  static constexpr int STAGE_BYTES = 2 * (OP32 + 2 * OP16);  // 64 KB / 32 KB
+  static constexpr int SMEM = P2_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int CTAS_PER_SM = BK == 32 ? 1 : 2;
+  static_assert(4 * 32 * P2_LDS_ROW * 4 + 4 * P2_TILE * 4 <= P2_STAGES * STAGE_BYTES, "epilogue staging must fit in the idle ring");
+};
+
+// UMMA descriptors of the operand tiles of one stage, k-step ks (one MMA: 8 floats / 16 bf16 of K).
+//   FP32 K-major : rows of BK*4 bytes, SWIZZLE_128B (BK = 32) / SWIZZLE_64B (BK = 16), 8-row atoms (SBO), step +32 B
+//   FP32 MN-major: SWIZZLE_128B_BASE32B, column blocks of [BK k-rows x 128 B] (LBO), atoms of 4 k-rows (SBO 512),
+//                  step = 8 k-rows = +1024 B
+//   BF16 K-major : rows of BK*2 bytes, SWIZZLE_64B (BK = 32, step +32 B) / SWIZZLE_32B (BK = 16, a single step)
+//   BF16 MN-major: SWIZZLE_128B, column blocks of [BK k-rows x 128 B = 64 bf16] (LBO), atoms of 8 k-rows (SBO 1024),
+//                  step = 16 k-rows = +2048 B
+template <int BK>
+__device__ __forceinline__ uint64_t desc32(uint32_t base, int mn_major, int ks) {
+  return mn_major ? smem_desc(base + ks * 1024, BK * 128, 512, 1) : smem_desc(base + ks * 32, 16, 8 * BK * 4, BK == 32 ? 2u : 4u);
+}
+template <int BK>
+__device__ __forceinline__ uint64_t desc16(uint32_t base, int mn_major, int ks) {
+  return mn_major ? smem_desc(base + ks * 2048, BK * 128, 1024, 2) : smem_desc(base + ks * 32, 16, 8 * BK * 2, BK == 32 ? 4u : 6u);
+}
+
+// optional phase trace (tools/tc2_trace.py): per CTA, %globaltimer at [0] entry [1] prologue done [2] first stage
+// landed (leader's MMA thread) [3] accumulator complete [4] first 128 columns staged [5] first 128 columns stored
+// [6] all stored [7] pair released
+__device__ unsigned long long* g_tc2_trace = nullptr;
+__device__ __forceinline__ void tc2_mark(int slot, bool who) {
+  if (g_tc2_trace && who) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (cta < 4096) g_tc2_trace[(size_t)cta * 8 + slot] = t;
+  }
+}
 
 struct Tc2Maps {
   CUtensorMap m[2][2][3];  // [pair][A | B][fp32 | hi | lo]
@@ -49,34 +94,17 @@ struct Tc2Args {
   int a_mn[2], b_mn[2];  // 1 = operand is MN-contiguous in global memory (MN-major UMMA operand)
 };
 
-// Half of a B operand form set (64 rows at k0), multicast to the CTAs of `mask`: with two pairs per cluster the pairs
-// compute vertically adjacent tiles, share the B tile, and each CTA fetches a quarter of it for itself and for its
-// counterpart in the other pair -- 96 KB instead of 128 KB per pair and k-block come out of the L2, which is what
-// bounds the single-pair kernel on a full chip (profiles/r2_summary.md).
-__device__ __forceinline__ void load_half_multicast(uint32_t dst32, uint32_t dst_hi, uint32_t dst_lo, const CUtensorMap* maps, int mn_major,
-                                                    int row0, int k0, uint32_t bar, uint16_t mask) {
-  if (mn_major) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) tma_load_2d_pair_mc(dst32 + j * (BKT * 128), &maps[0], row0 + 32 * j, k0, bar, mask);
-    tma_load_2d_pair_mc(dst_hi, &maps[1], row0, k0, bar, mask);
-    tma_load_2d_pair_mc(dst_lo, &maps[2], row0, k0, bar, mask);
-  } else {
-    tma_load_2d_pair_mc(dst32, &maps[0], k0, row0, bar, mask);
-    tma_load_2d_pair_mc(dst_hi, &maps[1], k0, row0, bar, mask);
-    tma_load_2d_pair_mc(dst_lo, &maps[2], k0, row0, bar, mask);
-  }
-}
-
 // one operand form set of 128 rows at k0: FP32 tile + the two BF16 planes
+template <int BK>
 __device__ __forceinline__ void load_operand(uint32_t dst32, uint32_t dst_hi, uint32_t dst_lo, const CUtensorMap* maps, int mn_major,
                                              int row0, int k0, uint32_t bar) {
   if (mn_major) {
 #pragma unroll
-    for (int j = 0; j < P2_ROWS / 32; ++j) tma_load_2d_pair(dst32 + j * (BKT * 128), &maps[0], row0 + 32 * j, k0, bar);
+    for (int j = 0; j < P2_ROWS / 32; ++j) tma_load_2d_pair(dst32 + j * (BK * 128), &maps[0], row0 + 32 * j, k0, bar);
 #pragma unroll
     for (int j = 0; j < P2_ROWS / 64; ++j) {
-      tma_load_2d_pair(dst_hi + j * (BKT * 128), &maps[1], row0 + 64 * j, k0, bar);
-      tma_load_2d_pair(dst_lo + j * (BKT * 128), &maps[2], row0 + 64 * j, k0, bar);
+      tma_load_2d_pair(dst_hi + j * (BK * 128), &maps[1], row0 + 64 * j, k0, bar);
+      tma_load_2d_pair(dst_lo + j * (BK * 128), &maps[2], row0 + 64 * j, k0, bar);
     }
   } else {
     tma_load_2d_pair(dst32, &maps[0], k0, row0, bar);
@@ -85,40 +113,42 @@ __device__ __forceinline__ void load_operand(uint32_t dst32, uint32_t dst_hi, ui
   }
 }
 
-// PAIRS = 1: cluster = one CTA pair.  PAIRS = 2: cluster = two pairs on vertically adjacent tiles sharing B by multicast.
-template <int PAIRS>
-__global__ void __launch_bounds__(P2_THREADS, 1)
+template <int BK>
+__global__ void __launch_bounds__(P2_THREADS, P2Cfg<BK>::CTAS_PER_SM)
 gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc2Args p) {
+  using Cfg = P2Cfg<BK>;
   const GemmArgs& g = p.g;
-  if (g.skip && *g.skip) return;  // uniform across the cluster: solver already terminated
-  const uint32_t crank = cluster_ctarank();
-  const uint32_t rank = crank & 1;     // 0 = leader of its pair: issues the MMAs for both CTAs
-  const uint32_t pair_id = crank >> 1;  // which pair of the cluster
+  if (g.skip && *g.skip) return;  // uniform across the pair: solver already terminated
+  const uint32_t rank = cluster_ctarank();  // 0 = leader: issues the MMAs for both CTAs
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(tiles + P2_STAGES * P2_STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(tiles + P2_STAGES * Cfg::STAGE_BYTES);
   uint64_t* full = bars;                    // [STAGES] leader's: bytes of BOTH CTAs landed
   uint64_t* empty = bars + P2_STAGES;       // [STAGES] MMAs reading the stage retired (commit multicast: both CTAs)
   uint64_t* acc_full = bars + 2 * P2_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tc2_mark(0, threadIdx.x == 0);
   // the two CTAs of a cluster are neighbours in x: blockIdx.x counts 128-row blocks, blockIdx.y 256-column tiles
   const int m0 = blockIdx.x * P2_ROWS;
   const int n0 = blockIdx.y * P2_TILE;
   const int nb0 = n0 + (int)rank * P2_ROWS;  // first row of B this CTA stages
   const int k_begin = blockIdx.z * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
-  const int n_kb = k_end > k_begin ? (k_end - k_begin + BKT - 1) / BKT : 0;
+  const int n_kb = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
   const int total = n_kb * g.n_pairs;
 
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < P2_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], PAIRS);  // a stage is refilled by multicast from both pairs: both must have drained it
+      mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 12; ++i)  // hide the descriptor fetch of the first loads
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i / 6][(i / 3) % 2][i % 3]) : "memory");
   }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(P2_TILE) : "memory");
@@ -128,28 +158,23 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc
   cluster_sync_all();  // the leader's barriers exist before the peer's TMA counts bytes on them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  tc2_mark(1, threadIdx.x == 0);
 
   if (warp == 4) {
     // ---------------- TMA producer (both CTAs) ----------------
     if (lane == 0) {
+      const uint32_t bar0 = map_to_cta(&full[0], 0);  // the leader's barriers, as shared::cluster addresses
       for (int it = 0; it < total; ++it) {
         const int s = it % P2_STAGES, ph = (it / P2_STAGES) & 1;
-        const int pr = it / n_kb, k0 = k_begin + (it % n_kb) * BKT;
+        const int pr = it / n_kb, k0 = k_begin + (it % n_kb) * BK;
         mbar_wait(&empty[s], ph ^ 1);
         // the leader arms its barrier for the bytes of both CTAs; the peer's complete_tx may arrive first (the phase
         // cannot complete before the leader's own arrival)
-        if (rank == 0) mbar_expect_tx(&full[s], 2 * P2_STAGE_BYTES);
-        const uint32_t bar = map_to_cta(&full[s], crank & ~1u);  // this pair's leader
-        const uint32_t base = smem_u32(tiles + s * P2_STAGE_BYTES);
-        load_operand(base + P2_A32, base + P2_AHI, base + P2_ALO, maps.m[pr][0], p.a_mn[pr], m0, k0, bar);
-        if (PAIRS == 1) {
-          load_operand(base + P2_B32, base + P2_BHI, base + P2_BLO, maps.m[pr][1], p.b_mn[pr], nb0, k0, bar);
-        } else {
-          // rows [nb0 + 64 pair_id, +64) of B for this CTA and for the CTA of the same pair rank in the other pair
-          const uint16_t mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
-          load_half_multicast(base + P2_B32 + pair_id * 8192, base + P2_BHI + pair_id * 4096, base + P2_BLO + pair_id * 4096,
-                              maps.m[pr][1], p.b_mn[pr], nb0 + 64 * (int)pair_id, k0, bar, mask);
-        }
+        if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+        const uint32_t bar = bar0 + s * 8;
+        const uint32_t base = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+        load_operand<BK>(base + Cfg::A32, base + Cfg::AHI, base + Cfg::ALO, maps.m[pr][0], p.a_mn[pr], m0, k0, bar);
+        load_operand<BK>(base + Cfg::B32, base + Cfg::BHI, base + Cfg::BLO, maps.m[pr][1], p.b_mn[pr], nb0, k0, bar);
       }
     }
   } else if (warp == 5) {
@@ -158,49 +183,55 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc
       for (int it = 0; it < total; ++it) {
         const int s = it % P2_STAGES, ph = (it / P2_STAGES) & 1, pr = it / n_kb;
         mbar_wait(&full[s], ph);
+        if (it == 0) tc2_mark(2, true);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int a_mn = p.a_mn[pr], b_mn = p.b_mn[pr];
         const uint32_t idesc32 = umma_idesc(2u, a_mn, b_mn, P2_TILE, P2_TILE), idesc16 = umma_idesc(1u, a_mn, b_mn, P2_TILE, P2_TILE);
-        const uint32_t base = smem_u32(tiles + s * P2_STAGE_BYTES);
+        const uint32_t base = smem_u32(tiles + s * Cfg::STAGE_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < BKT / 8; ++ks)
-          umma2_tf32(tmem_base, operand_desc(base + P2_A32, a_mn, ks), operand_desc(base + P2_B32, b_mn, ks), idesc32, (it | ks) != 0);
+        for (int ks = 0; ks < BK / 8; ++ks)
+          umma2_tf32(tmem_base, desc32<BK>(base + Cfg::A32, a_mn, ks), desc32<BK>(base + Cfg::B32, b_mn, ks), idesc32, (it | ks) != 0);
 #pragma unroll
-        for (int ks = 0; ks < BKT / 16; ++ks) {
-          umma2_bf16(tmem_base, corr_desc(base + P2_ALO, a_mn, ks), corr_desc(base + P2_BHI, b_mn, ks), idesc16, 1);
-          umma2_bf16(tmem_base, corr_desc(base + P2_AHI, a_mn, ks), corr_desc(base + P2_BLO, b_mn, ks), idesc16, 1);
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          umma2_bf16(tmem_base, desc16<BK>(base + Cfg::ALO, a_mn, ks), desc16<BK>(base + Cfg::BHI, b_mn, ks), idesc16, 1);
+          umma2_bf16(tmem_base, desc16<BK>(base + Cfg::AHI, a_mn, ks), desc16<BK>(base + Cfg::BLO, b_mn, ks), idesc16, 1);
         }
-        umma2_commit(&empty[s], (uint16_t)((1u << (2 * PAIRS)) - 1));  // one arrival in every CTA of the cluster
+        umma2_commit(&empty[s]);  // frees the stage in both CTAs
       }
-      umma2_commit(acc_full, (uint16_t)(3u << (2 * pair_id)));
+      umma2_commit(acc_full);
     }
   } else {
     // ---------------- epilogue (both CTAs: 128 rows x 256 columns each) ----------------
     // TMEM -> registers (one accumulator row per lane) -> shared (the ring is idle once acc_full fired: every MMA of
-    // the pair has retired and every TMA box was consumed) -> row-wise coalesced fused epilogue.
+    // the pair has retired and every TMA box was consumed) -> row-wise coalesced fused epilogue; 128 columns per pass.
     if (total > 0) {
       mbar_wait(acc_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    tc2_mark(3, threadIdx.x == 0);
     const uint32_t stage = smem_u32(tiles) + warp * 32 * P2_LDS_ROW * 4;
-#pragma unroll 2
-    for (int c = 0; c < P2_TILE; c += 16) {
-      float v[16];
-      if (total > 0) {
-        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + (lane * P2_LDS_ROW + c + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-    }
-    __syncwarp();
     float cs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // column sums of what this lane stores
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-      epilogue_dispatch<P2_LDS_ROW>(g, stage, h * 128 + lane * 4, m0 + warp * 32, n0 + h * 128 + lane * 4, cs[h]);
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll 2
+      for (int c = 0; c < 128; c += 16) {
+        float v[16];
+        if (total > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + h * 128 + c, v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + (lane * P2_LDS_ROW + c + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+      }
+      __syncwarp();
+      if (h == 0) tc2_mark(4, threadIdx.x == 0);
+      epilogue_dispatch<P2_LDS_ROW>(g, stage, lane * 4, m0 + warp * 32, n0 + h * 128 + lane * 4, cs[h]);
+      __syncwarp();  // the warp's staging rows are rewritten by the next pass
+      tc2_mark(5 + h, threadIdx.x == 0);
+    }
     if (g.colpart && m0 < g.M) {  // (the grid is padded to whole pairs: a CTA entirely below the matrix owns no row of colpart)
       // 4 warps x 32 rows -> one row of column sums per CTA (= per 128-row block, like gemm_tc.cu), fixed order
       float* red = reinterpret_cast<float*>(tiles) + 4 * 32 * P2_LDS_ROW;
@@ -216,6 +247,7 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();  // neither CTA leaves (or frees TMEM, or lets its shared memory go) while the pair is in flight
+  tc2_mark(7, threadIdx.x == 0);
   if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(P2_TILE) : "memory");
 }
 
@@ -300,27 +332,57 @@ int tc2_mode() {
   return mode;
 }
 
-static int operand_maps(CUtensorMap* out, const Operand& op, int MN, int K, int box_rows) {
+static int operand_maps(CUtensorMap* out, const Operand& op, int MN, int K, int bk) {
   const bool mn_major = op.s_k != 1;
   const CUtensorMap* m[3];
   if (mn_major) {
-    m[0] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, op.ptr, (uint64_t)MN, (uint64_t)K, (uint64_t)op.s_k * 4, 32, BKT,
+    m[0] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, op.ptr, (uint64_t)MN, (uint64_t)K, (uint64_t)op.s_k * 4, 32, (uint32_t)bk,
                              CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     for (int i = 0; i < 2; ++i)
       m[1 + i] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op.img.hi + i * op.img.plane, (uint64_t)MN, (uint64_t)K,
-                                   (uint64_t)op.img.ld * 2, 64, BKT, CU_TENSOR_MAP_SWIZZLE_128B);
+                                   (uint64_t)op.img.ld * 2, 64, (uint32_t)bk, CU_TENSOR_MAP_SWIZZLE_128B);
   } else {
-    m[0] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, op.ptr, (uint64_t)K, (uint64_t)MN, (uint64_t)op.s_mn * 4, BKT,
-                             (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+    m[0] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, op.ptr, (uint64_t)K, (uint64_t)MN, (uint64_t)op.s_mn * 4, (uint32_t)bk,
+                             P2_ROWS, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     for (int i = 0; i < 2; ++i)
       m[1 + i] = cached_tensor_map(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op.img.hi + i * op.img.plane, (uint64_t)K, (uint64_t)MN,
-                                   (uint64_t)op.img.ld * 2, BKT, (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_64B);
+                                   (uint64_t)op.img.ld * 2, (uint32_t)bk, P2_ROWS, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   }
   for (int i = 0; i < 3; ++i) {
     if (!m[i]) return HF_ERR_CUDA;
     out[i] = *m[i];
   }
   return HF_OK;
+}
+
+int set_tc2_trace(void* d_buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(d_buf);
+  HF_CUDA(cudaMemcpyToSymbol(g_tc2_trace, &p, sizeof(p)));
+  return HF_OK;
+}
+
+template <int BK>
+static int launch_bk(const Tc2Maps& maps, const Tc2Args& p, dim3 grid, cudaStream_t stream) {
+  static bool seen[64] = {};
+  if (first_use_on_device(seen))
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<BK>::SMEM));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = dim3(P2_THREADS), cfg.dynamicSmemBytes = P2Cfg<BK>::SMEM, cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  HF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BK>, maps, p));
+  note_launch();
+  return HF_OK;
+}
+
+// k-block width of a launch.  BK = 32 (one CTA per SM) unless HF_TC2_BK=16 asks for the co-resident build: measured on
+// B200 (tools/tc2_trace.py, 7500x1000x784) the two give the same time, 53 vs 55 us -- co-resident pairs start together,
+// share the tensor pipe at half rate each, reach their epilogues together, and nothing overlaps.
+int tc2_block_k(int, int, int) {
+  static const int forced = getenv("HF_TC2_BK") ? atoi(getenv("HF_TC2_BK")) : 0;
+  return forced == 16 ? 16 : 32;
 }
 
 int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t stream) {
@@ -331,38 +393,18 @@ int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t stream) {
   if (g.split_k < 1) g.split_k = 1;
   if (g.split_k == 1) g.k_per_split = ((g.K + BKT - 1) / BKT) * BKT;
   HF_REQUIRE(g.k_per_split % BKT == 0, HF_ERR_INVALID, "tcgen05 engine: K split must be a multiple of %d", BKT);
-  // HF_TC2_MC=1: two pairs per cluster with B shared by multicast, when the tile rows pair up without much padding.
-  // Parity-green, but measured no faster on B200 (main loop 1.12 vs 0.97 us per k-block on a full chip, 132 instead of
-  // 148 SMs usable by 4-CTA clusters of this size): a multicast to <= 4 CTAs does not lower the L2 -> SM traffic that
-  // bounds the loop (profiles/r2_summary.md), so single-pair clusters are the default.
-  static const bool mc_allowed = getenv("HF_TC2_MC") && atoi(getenv("HF_TC2_MC")) != 0;
-  const int tiles_m = (g.M + P2_TILE - 1) / P2_TILE;
-  const int pairs = (mc_allowed && (tiles_m % 2 == 0 || tiles_m >= 9)) ? 2 : 1;
+  const int bk = tc2_block_k(g.M, g.N, g.split_k);
   Tc2Maps maps;
   for (int s = 0; s < 2; ++s) {
     const int src = s < g.n_pairs ? s : 0;
     p.a_mn[s] = g.A[src].s_k != 1, p.b_mn[s] = g.B[src].s_k != 1;
-    int rc = operand_maps(maps.m[s][0], g.A[src], g.M, g.K, P2_ROWS);
+    int rc = operand_maps(maps.m[s][0], g.A[src], g.M, g.K, bk);
     if (rc) return rc;
-    rc = operand_maps(maps.m[s][1], g.B[src], g.N, g.K, P2_ROWS / pairs);  // multicast: each CTA fetches 64 rows of B
+    rc = operand_maps(maps.m[s][1], g.B[src], g.N, g.K, bk);
     if (rc) return rc;
   }
-  static bool seen[64] = {};
-  if (first_use_on_device(seen)) {
-    HF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
-    HF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs * ((tiles_m + pairs - 1) / pairs), (g.N + P2_TILE - 1) / P2_TILE, g.split_k);
-  cfg.blockDim = dim3(P2_THREADS), cfg.dynamicSmemBytes = P2_SMEM, cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2 * pairs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-  cfg.attrs = at, cfg.numAttrs = 1;
-  if (pairs == 2) HF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<2>, maps, p));
-  else HF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<1>, maps, p));
-  note_launch();
-  return HF_OK;
+  const dim3 grid(2 * ((g.M + P2_TILE - 1) / P2_TILE), (g.N + P2_TILE - 1) / P2_TILE, g.split_k);
+  return bk == 32 ? launch_bk<32>(maps, p, grid, stream) : launch_bk<16>(maps, p, grid, stream);
 }
 
 }  // namespace hf

@@ -1216,6 +1216,7 @@ int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t ac
 }
 
 int hf_debug_tc_trace(void* d_buf) { return set_tc_trace(d_buf); }
+int hf_debug_tc2_trace(void* d_buf) { return set_tc2_trace(d_buf); }
 int hf_debug_tc_trace_iters(void* d_buf) { return set_tc_trace_iters(d_buf); }
 
 size_t hf_contract_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t n_pairs) {

@@ -49,16 +49,6 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
-// the same box delivered to the same shared-memory offset of every CTA in `cta_mask` (one L2 read feeds them all); the
-// bytes are counted, per destination CTA, on the barrier that stands in the same self/peer relation to it as
-// `bar_cluster` does to the issuing CTA -- with bar_cluster = the issuer's pair leader: on every destination's leader
-__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster,
-                                                    uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
-      "l"(map), "r"(bar_cluster), "h"(cta_mask), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

@@ -8,6 +8,7 @@ chunk sum (gradient once per step, curvature product once per CG iteration, cand
 per batch of candidates).  Every rank then runs the identical fused vector update, so the replicas
 stay in lock-step without any scalar collective.
 """
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -34,7 +35,7 @@ class NativeProblem:
             else [net.linearize(x, t, loss_only=True) for x, t in loss_data]
         self.n_mvp, self.n_grad, self.n_loss = (self._count(l) for l in (self.mvp_lins, self.grad_lins, self.loss_lins))
         self._cand = torch.empty_like(theta)
-        self.overlap_allreduce = False
+        self.overlap_allreduce = os.environ.get("HF_OVERLAP_ALLREDUCE") == "1"
         off, cnt = net.first_layer_span()
         # the overlap split needs the first layer's slice to be a 16-byte aligned prefix of the flat vector
         self._split_at = cnt if (off == 0 and 0 < cnt < theta.numel() and cnt % 4 == 0) else 0

@@ -35,6 +35,9 @@ cases = [  # (M, N, K, layout, pairs, what)
     (7500, 1000, 784, KK, 1, "cfg3 R-op 1"), (7500, 500, 1000, KK, 2, "cfg3 R-op 2"), (7500, 784, 1000, KK, 2, "cfg3 R-op 8"),
     (7500, 1000, 784, KM, 1, "cfg3 transposed 8"), (1000, 784, 7500, MM, 1, "cfg3 weight grad 1 (unsplit)"),
     (60000, 1000, 784, KK, 1, "cfg3 R-op 1, one 60000 chunk"),
+    (7500, 250, 500, KK, 2, "cfg3 R-op 3 (narrow)"), (7500, 30, 250, KK, 2, "cfg3 R-op 4 (code layer)"), (7500, 250, 30, KK, 2, "cfg3 R-op 5"),
+    (7500, 500, 250, KK, 2, "cfg3 R-op 6"), (7500, 500, 250, KM, 1, "cfg3 transposed 3"), (7500, 250, 500, KM, 1, "cfg3 transposed 6"),
+    (250, 500, 7500, MM, 1, "cfg3 weight grad 3 (unsplit)"),
     (8192, 8192, 2048, KK, 1, "large square"), (16384, 4096, 4096, KK, 1, "large"),
 ]
 for M, N, K, lay, pairs, what in cases:
