@@ -35,7 +35,11 @@ class NativeProblem:
             else [net.linearize(x, t, loss_only=True) for x, t in loss_data]
         self.n_mvp, self.n_grad, self.n_loss = (self._count(l) for l in (self.mvp_lins, self.grad_lins, self.loss_lins))
         self._cand = torch.empty_like(theta)
-        self.overlap_allreduce = os.environ.get("HF_OVERLAP_ALLREDUCE") == "1"
+        # Overlap the all-reduce of the upper layers' slices with the first layer's weight gradient (see matvec).  Pays
+        # once the vector is large: measured on 8 B200 at P = 2.8 M (autoencoder) 697 vs 660 products/s, at P = 0.67 M
+        # (MLP) two collectives cost more fixed latency than the overlap hides.  HF_OVERLAP_ALLREDUCE=0/1 overrides.
+        env = os.environ.get("HF_OVERLAP_ALLREDUCE")
+        self.overlap_allreduce = (env == "1") if env in ("0", "1") else theta.numel() >= 2_000_000
         off, cnt = net.first_layer_span()
         # the overlap split needs the first layer's slice to be a 16-byte aligned prefix of the flat vector
         self._split_at = cnt if (off == 0 and 0 < cnt < theta.numel() and cnt % 4 == 0) else 0
@@ -86,10 +90,10 @@ class NativeProblem:
         """``out = B v`` (no damping), enqueued without host synchronisation.
 
         Data-parallel: one all-reduce(sum) of the flat vector after the local chunk sum.  With
-        ``overlap_allreduce`` (off by default) and one chunk per rank the sweep runs in two phases and the
+        ``overlap_allreduce`` (default for P >= 2 M) and one chunk per rank the sweep runs in two phases and the
         all-reduce of the upper layers' slices (final after phase 0) overlaps with the first layer's weight
-        gradient.  Measured on 4 B200 with NCCL at cfg2's P = 669 706: two collectives cost more fixed latency than
-        the overlap hides (16.6 vs 14.6 ms per 50-iteration solve), hence the default."""
+        gradient, the last and largest contraction of the sweep.  Both forms sum the same per-rank vectors with the
+        same collective, so replicas stay bit-identical either way."""
         if self.overlap_allreduce and self.group is not None and len(self.mvp_lins) == 1 and self._split_at > 0:
             import torch.distributed as dist
 
