@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define HF_ABI_VERSION 1
+#define HF_ABI_VERSION 2
 
 enum hf_status {
   HF_OK = 0,
@@ -156,6 +156,14 @@ int hf_axpy_out(int dtype, int64_t P, const void* d_a, double alpha, const void*
 typedef struct hf_net hf_net_t;
 typedef struct hf_lin hf_lin_t;
 
+/* HF_LAYER_CONV2D: nn.Conv2d(c_in, out_features, (k_h, k_w), stride, pad) on an [h_in, w_in] map; in_features must be
+ * c_in*k_h*k_w, the weight [out, c_in, k_h, k_w] sits at w_offset exactly as PyTorch flattens it, inputs are NCHW when it
+ * is the first layer.  HF_LAYER_AVGPOOL: average over the whole [h_in, w_in] map (in_features = out_features = c_in, no
+ * parameters); the layers after it see one row per sample again.  The last layer must produce one row per sample.
+ * Conv nets support loss, gradient and GGN products (examples/run_allcnnc_cifar100_deepobs.py, eval mode); Hessian
+ * products and the Fisher diagonal of conv nets are not lowered yet (HF_ERR_UNSUPPORTED). */
+enum hf_layer_kind { HF_LAYER_LINEAR = 0, HF_LAYER_CONV2D = 1, HF_LAYER_AVGPOOL = 2 };
+
 typedef struct {
   int32_t in_features;
   int32_t out_features;
@@ -165,6 +173,10 @@ typedef struct {
   int64_t b_offset;     /* offset of bias[out], -1 = frozen or absent                     */
   const float* d_w_frozen; /* device pointer to the weight when w_offset < 0              */
   const float* d_b_frozen; /* device pointer to the bias when has_bias && b_offset < 0    */
+  int32_t kind;         /* hf_layer_kind; 0 = fully connected (the fields below are ignored) */
+  int32_t c_in, h_in, w_in;
+  int32_t k_h, k_w, stride, pad;
+  int32_t h_out, w_out;
 } hf_layer_desc;
 
 /* n_params = length P of the flat trainable vector. */

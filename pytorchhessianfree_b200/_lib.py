@@ -11,7 +11,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libhf_b200.so")
 
+ABI_VERSION = 2
 HF_F32, HF_F64 = 0, 1
+LAYER_KIND = {"linear": 0, "conv2d": 1, "avgpool": 2}
 ACT = {"none": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 LOSS = {"mse": 0, "ce": 1, "bce": 2}
 REDUCTION = {"mean": 0, "sum": 1}
@@ -41,6 +43,9 @@ class LayerDesc(C.Structure):
     _fields_ = [
         ("in_features", C.c_int32), ("out_features", C.c_int32), ("act", C.c_int32), ("has_bias", C.c_int32),
         ("w_offset", C.c_int64), ("b_offset", C.c_int64), ("d_w_frozen", C.c_void_p), ("d_b_frozen", C.c_void_p),
+        ("kind", C.c_int32), ("c_in", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32),
+        ("k_h", C.c_int32), ("k_w", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("h_out", C.c_int32), ("w_out", C.c_int32),
     ]
 
 
@@ -108,8 +113,8 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.hf_abi_version() != 1:
-        raise RuntimeError(f"{path}: ABI version {lib.hf_abi_version()} != 1; rebuild")
+    if lib.hf_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI version {lib.hf_abi_version()} != {ABI_VERSION}; rebuild")
     _lib = lib
     return lib
 

@@ -15,6 +15,7 @@
 #include <new>
 #include <vector>
 
+#include "conv.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "head.cuh"
@@ -26,6 +27,10 @@ struct Layer {
   int64_t w_off, b_off;
   const float* w_frozen;
   const float* b_frozen;
+  int kind;       // hf_layer_kind.  CONV2D: in = c_in*k_h*k_w, the contraction runs on the unfolded input (conv.cuh)
+  ConvGeom geom;  // CONV2D / AVGPOOL
+  int s_in, s_out;  // rows (positions) per sample of the layer's input / output activation: 1 for fully connected layers
+  bool unfold;    // CONV2D whose unfolded input is not the input itself (anything but 1x1, stride 1, no padding)
 };
 
 }  // namespace hf
@@ -39,6 +44,9 @@ struct hf_net {
   int classes;
   int engine;  // 0 = SIMT everywhere, 1 = tcgen05 where the shape allows
   bool has_relu;
+  bool has_conv;   // any CONV2D / AVGPOOL layer: activations have more rows than samples
+  int max_s;       // largest rows-per-sample of any activation
+  int64_t max_act; // largest floats-per-sample of any [rows, width] matrix a product touches (activations, unfolded inputs)
 };
 
 struct hf_lin {
@@ -91,6 +99,13 @@ struct hf_lin {
   // which one split pass writes here (FP32 with a 16-byte pitch, + images when the linearisation keeps them).
   float* sq[2];
   ImgBuf sq_img[2];
+  // conv layers (conv.cuh): the input in position-major layout when the first layer is a convolution, the unfolded
+  // input U_l of every layer that needs one (constant for the life of the linearisation), and two scratch matrices of
+  // the largest unfolded size: the unfolded tangent of the R-op and dU = cot W of the transposed sweep
+  float* xn;
+  std::vector<float*> U;
+  float* ru;
+  float* du;
   const float* pending_cur;   // phased sweep: cotangent of the first trainable layer, left by phase 0 for phase 1
   int pending_cols;
   cudaStream_t side;          // weight/bias gradients of layer l run here, concurrently with the data product that
@@ -133,6 +148,26 @@ static Image16 image_for(const hf_lin* lin, const float* base, int width) {
 static Operand with_image(const hf_lin* lin, Operand op, int width) {
   op.img = image_for(lin, op.ptr, width);
   return op;
+}
+
+// rows of the activation layer l writes / reads: samples x positions per sample (1 for fully connected layers)
+static inline int64_t rows_out(const hf_lin* lin, int l) { return lin->N * lin->net->L[l].s_out; }
+static inline int64_t rows_in(const hf_lin* lin, int l) { return lin->N * lin->net->L[l].s_in; }
+
+// The [rows_out(l), L.in] matrix layer l contracts with its weight: the unfolded input of a convolution, the input
+// itself otherwise (position-major copy of x when a convolution comes first).  *ld receives its row pitch.
+static const float* layer_input(const hf_lin* lin, int l, int* ld) {
+  const hf::Layer& L = lin->net->L[l];
+  if (L.unfold) {
+    *ld = pad4(L.in);
+    return lin->U[l];
+  }
+  if (l == 0) {
+    *ld = L.kind == HF_LAYER_LINEAR ? L.in : pad4(L.in);
+    return L.kind == HF_LAYER_LINEAR ? lin->x : lin->xn;
+  }
+  *ld = pad4(L.in);
+  return lin->a[l - 1];
 }
 
 // ---- row-wise loss kernels ---------------------------------------------------------------------
@@ -413,17 +448,17 @@ static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream, b
 // out_b[out] (+)= scale * column sums of d.  The column sums either come for free from the tensor-core kernel that
 // produced d (`col_tiles` partial rows already in lin->colbuf) or from one colsum launch; ONE launch then reduces
 // both partial sets in fixed order (deterministic) into the flat vector.
-static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
+static int layer_gradient(hf_lin* lin, int64_t rows, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
                           float* out_w, const float* d, int ld_d, int col_tiles, float* colbuf, float* out_b, float scale,
                           int accumulate, const int32_t* skip, cudaStream_t stream, bool main_scratch = false) {
   int splits_w = 0, splits_b = 0;
   float* const partial = main_scratch ? lin->partial_main : lin->partial;
   if (out_w) {
     GemmArgs g = blank_gemm();
-    g.M = M, g.N = N, g.K = (int)lin->N, g.n_pairs = n_pairs;
+    g.M = M, g.N = N, g.K = (int)rows, g.n_pairs = n_pairs;
     for (int s = 0; s < n_pairs; ++s) g.A[s] = A[s], g.B[s] = B[s];
     int gemm_square = square;  // (the bias slice below still needs `square` for its column sums)
-    if (square && lin->sq[0] && n_pairs == 1 && A[0].s_mn == 1 && B[0].s_mn == 1 && (int64_t)M * N * lin->N >= kTcMinWork) {
+    if (square && lin->sq[0] && n_pairs == 1 && A[0].s_mn == 1 && B[0].s_mn == 1 && (int64_t)M * N * rows >= kTcMinWork) {
       // Fisher diagonal as a tensor-core contraction: square the two operands once (one launch), contract as usual
       SplitTable t;
       t.count = 2, t.skip = skip;
@@ -432,7 +467,7 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
         const Operand& src = w ? B[0] : A[0];
         const int cols = w ? N : M;
         const Image16 im = lin->sq_img[w].hi ? Image16{lin->sq_img[w].hi, lin->sq_img[w].plane, pad8(cols)} : Image16{nullptr, 0, 0};
-        t.seg[w] = SplitSegment{src.ptr, lin->N, cols, src.s_k, lin->sq[w], pad4(cols), im, 1};
+        t.seg[w] = SplitSegment{src.ptr, rows, cols, src.s_k, lin->sq[w], pad4(cols), im, 1};
         sqop[w] = Operand{lin->sq[w], 1, pad4(cols), im};
       }
       int rcs = launch_split(t, stream);
@@ -441,13 +476,13 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
       gemm_square = 0;
     }
     g.square = gemm_square;
-    SplitPlan sp = plan_split(M, N, lin->N, weight_on_tensor(lin->net, M, N, lin->N, gemm_square));
+    SplitPlan sp = plan_split(M, N, rows, weight_on_tensor(lin->net, M, N, rows, gemm_square));
     int pair_hint = 0;
     if (lin->net->engine == 1 && tc2_mode() != 0 && tc2_supported(g)) {
       // both engines can take it: compare the modelled times of their own best split
       double us_pair = 0.0;
-      const SplitPlan sp2 = plan_split_pair(M, N, lin->N, &us_pair);
-      const double us_single = tc2_estimate(M, N, (int)lin->N, 1, sp.splits).us_single + 0.05 * sp.splits;
+      const SplitPlan sp2 = plan_split_pair(M, N, rows, &us_pair);
+      const double us_single = tc2_estimate(M, N, (int)rows, 1, sp.splits).us_single + 0.05 * sp.splits;
       if (tc2_mode() == 2 || us_pair < 0.9 * us_single) sp = sp2, pair_hint = 1;
     }
     HF_REQUIRE((size_t)sp.splits * M * N <= (main_scratch ? lin->partial_main_floats : lin->partial_floats), HF_ERR_WORKSPACE,
@@ -464,10 +499,10 @@ static int layer_gradient(hf_lin* lin, int M, int N, int n_pairs, const Operand*
     if (col_tiles > 0) {
       splits_b = col_tiles;
     } else {
-      splits_b = colsum_plan(lin->N);
-      const int rows_per = (int)((lin->N + splits_b - 1) / splits_b);
+      splits_b = colsum_plan(rows);
+      const int rows_per = (int)((rows + splits_b - 1) / splits_b);
       HF_REQUIRE((size_t)splits_b <= lin->col_rows, HF_ERR_WORKSPACE, "column-sum scratch too small");
-      colsum_kernel<<<dim3((M + 31) / 32, splits_b), dim3(32, 8), 0, stream>>>(d, lin->N, M, ld_d, rows_per, square,
+      colsum_kernel<<<dim3((M + 31) / 32, splits_b), dim3(32, 8), 0, stream>>>(d, rows, M, ld_d, rows_per, square,
                                                                                 colbuf, skip);
       HF_LAUNCH_CHECK();
     }
@@ -525,17 +560,37 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
   if (rcp) return rcp;
   for (int l = net->first_trainable; l < l_end; ++l) {
     const Layer& L = net->L[l];
-    const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
-    const int ld_in = l == 0 ? L.in : pad4(L.in), ld_out = pad4(L.out);
+    const int ld_out = pad4(L.out);
+    if (L.kind == HF_LAYER_AVGPOOL) {
+      // the tangent of a global average pool is the pool of the tangent
+      if (cur) {
+        float* dst = lin->buf[which];
+        avgpool_kernel<<<conv_blocks(lin->N * (int64_t)L.out), 256, 0, stream>>>(cur, ld_out, dst, lin->N, L.s_in, L.out,
+                                                                                  image_for(lin, dst, L.out), skip);
+        HF_LAUNCH_CHECK();
+        cur = dst;
+        which ^= 1;
+      }
+      continue;
+    }
+    int ld_in = 0;
+    const float* a_in = layer_input(lin, l, &ld_in);
     GemmArgs g = blank_gemm();
-    g.M = (int)lin->N, g.N = L.out, g.K = L.in;
+    g.M = (int)rows_out(lin, l), g.N = L.out, g.K = L.in;
     int np = 0;
     if (L.w_off >= 0) {
       g.A[np] = with_image(lin, op_kc(a_in, ld_in), L.in), g.B[np] = v_operand(lin, l, v, true);
       ++np;
     }
     if (cur) {
-      g.A[np] = with_image(lin, op_kc(cur, ld_in), L.in), g.B[np] = w_operand(lin, l, theta, true);
+      const float* cur_mat = cur;
+      if (L.unfold) {  // the tangent of the unfolded input is the unfolded tangent
+        im2col_kernel<<<conv_blocks(rows_out(lin, l) * L.geom.cin), 256, 0, stream>>>(cur, pad4(L.geom.cin), lin->ru, pad4(L.in), lin->N, L.geom,
+                                                                                     image_for(lin, lin->ru, L.in), skip);
+        HF_LAUNCH_CHECK();
+        cur_mat = lin->ru;
+      }
+      g.A[np] = with_image(lin, op_kc(cur_mat, pad4(L.in)), L.in), g.B[np] = w_operand(lin, l, theta, true);
       ++np;
     }
     float* dst = (hessian && l < nl - 1) ? lin->ra[l] : lin->buf[which];
@@ -564,11 +619,11 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
     }
     if (np == 0) {
       // a frozen layer fed by a zero tangent contributes only its (frozen) nothing: R{z} = 0
-      HF_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * lin->N * ld_out, stream));
+      HF_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * rows_out(lin, l) * ld_out, stream));
       const Image16 im = image_for(lin, dst, L.out);
       if (im.hi) {
-        HF_CUDA(cudaMemsetAsync(im.hi, 0, sizeof(uint16_t) * lin->N * im.ld, stream));
-        HF_CUDA(cudaMemsetAsync(im.hi + im.plane, 0, sizeof(uint16_t) * lin->N * im.ld, stream));
+        HF_CUDA(cudaMemsetAsync(im.hi, 0, sizeof(uint16_t) * rows_out(lin, l) * im.ld, stream));
+        HF_CUDA(cudaMemsetAsync(im.hi + im.plane, 0, sizeof(uint16_t) * rows_out(lin, l) * im.ld, stream));
       }
     } else {
       g.n_pairs = np;
@@ -700,8 +755,23 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       continue;
     }
     const Layer& L = net->L[l];
-    const float* a_in = l == 0 ? lin->x : lin->a[l - 1];
-    const int ld_in = l == 0 ? L.in : pad4(L.in), ld_out = pad4(L.out);
+    const int ld_out = pad4(L.out);
+    if (L.kind == HF_LAYER_AVGPOOL) {
+      // transposed global average pool: every position of the map receives cot / (h*w), through the activation
+      // derivative of the layer below (which the kernel producing cot[l-1] always applies)
+      if (l - 1 < net->first_trainable) break;  // nothing trainable below
+      const Layer& Lp = net->L[l - 1];
+      float* dst = lin->cot[l - 1];
+      unpool_kernel<<<conv_blocks(rows_out(lin, l - 1) * (int64_t)L.out), 256, 0, stream>>>(cur, ld_out, lin->a[l - 1], Lp.act, dst, lin->N, L.s_in,
+                                                                                            L.out, image_for(lin, dst, L.out), skip);
+      HF_LAUNCH_CHECK();
+      if (fork) HF_CUDA(cudaEventRecord(lin->ev[l - 1], stream));
+      cur = dst, cur_col_tiles = 0;
+      continue;
+    }
+    int ld_in = 0;
+    const float* a_in = layer_input(lin, l, &ld_in);
+    const int64_t rows = rows_out(lin, l);
     {
       Operand A[2], B[2];
       int np = 0;
@@ -714,7 +784,7 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       // it runs there (own split-K scratch) while the side stream finishes the upper layers' reductions.
       const bool on_main = fork && l == net->first_trainable && lin->partial_main != nullptr;
       if (fork && !on_main) HF_CUDA(cudaStreamWaitEvent(gstream, lin->ev[l], 0));
-      int rc = layer_gradient(lin, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
+      int rc = layer_gradient(lin, rows, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
                               cur_col_tiles, lin->colbuf[l], has_b ? out + L.b_off : nullptr, scale, accumulate, skip,
                               on_main ? stream : gstream, on_main);
       if (rc) return rc;
@@ -723,9 +793,27 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
     if (l > net->first_trainable) {
       const Layer& Lp = net->L[l - 1];
       GemmArgs g = blank_gemm();
-      g.M = (int)lin->N, g.N = L.in, g.K = L.out;
+      g.M = (int)rows, g.N = L.in, g.K = L.out;
       int np = 0;
       g.A[np] = with_image(lin, op_kc(cur, ld_out), L.out), g.B[np] = w_operand(lin, l, theta, false), ++np;
+      if (L.unfold) {
+        // convolution: dU = cot W is the cotangent of the UNFOLDED input; fold it back onto the input map (gather
+        // form) and apply the activation derivative of the layer below there
+        g.n_pairs = np;
+        g.C = lin->du, g.ldc = pad4(L.in);
+        g.epi = EPI_STORE;
+        g.skip = skip;
+        int rc = run_gemm(net, g, stream);
+        if (rc) return rc;
+        float* dst = lin->cot[l - 1];
+        fold_kernel<<<conv_blocks(rows_in(lin, l) * L.geom.cin), 256, 0, stream>>>(lin->du, pad4(L.in), lin->a[l - 1], pad4(L.geom.cin), Lp.act, dst,
+                                                                                  lin->N, L.geom, image_for(lin, dst, L.geom.cin), skip);
+        HF_LAUNCH_CHECK();
+        if (fork) HF_CUDA(cudaEventRecord(lin->ev[l - 1], stream));
+        cur = dst, cur_col_tiles = 0;
+        continue;
+      }
+      const int ld_in = pad4(L.in);  // (= the pitch of a[l-1] and cot[l-1])
       if (mode == BACK_HESSIAN && L.w_off >= 0) {
         g.A[np] = op_kc(lin->delta[l], ld_out), g.B[np] = v_operand(lin, l, v, false), ++np;
       }
@@ -743,7 +831,7 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
         g.C2 = (keep && curved(Lp.act)) ? lin->ga[l - 1] : nullptr;
       }
       g.skip = skip;
-      const int row_tiles = (int)((lin->N + 127) / 128);
+      const int row_tiles = (int)((rows + 127) / 128);
       const bool want_cols = !square && Lp.has_bias && Lp.b_off >= 0 && (size_t)row_tiles <= lin->col_rows;
       g.colpart = want_cols ? lin->colbuf[l - 1] : nullptr;
       bool on_tensor = false;
@@ -776,11 +864,13 @@ int hf_net_create(const hf_layer_desc* layers, int32_t n_layers, int32_t loss, i
   HF_REQUIRE(net, HF_ERR_INVALID, "hf_net_create: out of host memory");
   net->loss = loss, net->reduction = reduction, net->P = n_params;
   net->first_trainable = -1, net->max_width = 0, net->engine = 0, net->has_relu = false;
+  net->has_conv = false, net->max_s = 1, net->max_act = 0;
   for (int i = 0; i < n_layers; ++i) {
     const hf_layer_desc& d = layers[i];
     bool ok = d.in_features > 0 && d.out_features > 0 && d.act >= HF_ACT_NONE && d.act <= HF_ACT_TANH;
-    ok = ok && (i == 0 || d.in_features == layers[i - 1].out_features);
-    ok = ok && (d.w_offset >= 0 ? d.w_offset + (int64_t)d.in_features * d.out_features <= n_params : d.d_w_frozen != nullptr);
+    ok = ok && (i == 0 || d.kind != HF_LAYER_LINEAR || d.in_features == layers[i - 1].out_features);
+    ok = ok && (d.kind == HF_LAYER_AVGPOOL ||
+                (d.w_offset >= 0 ? d.w_offset + (int64_t)d.in_features * d.out_features <= n_params : d.d_w_frozen != nullptr));
     if (d.has_bias) ok = ok && (d.b_offset >= 0 ? d.b_offset + d.out_features <= n_params : d.d_b_frozen != nullptr);
     if (!ok) {
       delete net;
@@ -788,12 +878,46 @@ int hf_net_create(const hf_layer_desc* layers, int32_t n_layers, int32_t loss, i
     }
     Layer l{d.in_features, d.out_features, d.act, d.has_bias, d.w_offset, d.has_bias ? d.b_offset : -1, d.d_w_frozen,
             d.d_b_frozen};
+    l.kind = d.kind, l.s_in = l.s_out = 1, l.unfold = false;
+    l.geom = ConvGeom{d.c_in, d.h_in, d.w_in, d.k_h, d.k_w, d.stride, d.pad, d.h_out, d.w_out};
+    if (l.kind != HF_LAYER_LINEAR) {
+      const ConvGeom& g = l.geom;
+      bool cok = g.cin > 0 && g.hin > 0 && g.win > 0;
+      if (l.kind == HF_LAYER_CONV2D) {
+        cok = cok && g.kh > 0 && g.kw > 0 && g.stride > 0 && g.pad >= 0 && l.in == g.cin * g.kh * g.kw &&
+              g.hout == (g.hin + 2 * g.pad - g.kh) / g.stride + 1 && g.wout == (g.win + 2 * g.pad - g.kw) / g.stride + 1 && g.hout > 0 && g.wout > 0;
+        l.s_in = g.hin * g.win, l.s_out = g.hout * g.wout;
+        l.unfold = !(g.kh == 1 && g.kw == 1 && g.stride == 1 && g.pad == 0);
+      } else if (l.kind == HF_LAYER_AVGPOOL) {
+        cok = cok && l.in == g.cin && l.out == g.cin && !l.has_bias && l.w_off < 0 && l.act == HF_ACT_NONE && i > 0;
+        l.s_in = g.hin * g.win, l.s_out = 1;
+      } else {
+        cok = false;
+      }
+      // chaining: the feature map this layer reads is the one the previous layer wrote
+      if (i > 0) cok = cok && g.cin == net->L[i - 1].out && l.s_in == net->L[i - 1].s_out;
+      if (!cok) {
+        delete net;
+        HF_REQUIRE(false, HF_ERR_INVALID, "hf_net_create: layer %d: inconsistent convolution / pooling geometry", i);
+      }
+      net->has_conv = true;
+    } else if (i > 0 && net->L[i - 1].s_out != 1) {
+      delete net;
+      HF_REQUIRE(false, HF_ERR_UNSUPPORTED, "hf_net_create: layer %d: a fully connected layer needs one row per sample (pool first)", i);
+    }
     if (net->first_trainable < 0 && (l.w_off >= 0 || l.b_off >= 0)) net->first_trainable = i;
     if (l.act == HF_ACT_RELU) net->has_relu = true;
     net->max_width = std::max(net->max_width, std::max(l.in, pad4(l.out)));
+    net->max_s = std::max(net->max_s, std::max(l.s_in, l.s_out));
+    net->max_act = std::max(net->max_act, std::max((int64_t)l.s_out * pad4(l.out), (int64_t)l.s_out * pad4(l.in)));
+    if (i == 0) net->max_act = std::max(net->max_act, (int64_t)l.s_in * pad4(l.kind == HF_LAYER_LINEAR ? l.in : l.geom.cin));
     net->L.push_back(l);
   }
   net->classes = net->L.back().out;
+  if (net->L.back().s_out != 1) {
+    delete net;
+    HF_REQUIRE(false, HF_ERR_UNSUPPORTED, "hf_net_create: the last layer must produce one row per sample (add the average pool)");
+  }
   if (net->first_trainable < 0) {
     delete net;
     HF_REQUIRE(false, HF_ERR_INVALID, "hf_net_create: no trainable parameter");
@@ -837,8 +961,10 @@ static bool wants_images(const hf_net* net, int64_t N, int flags) {
   if (tc2_mode() == 2) return true;
   for (int l = net->first_trainable; l < (int)net->L.size(); ++l) {
     const Layer& L = net->L[l];
-    if ((int64_t)N * L.out * L.in < kTcMinWork || L.out < 96 || N < 192) continue;
-    const Tc2Choice c = tc2_estimate((int)N, L.out, L.in, 1, 1);
+    if (L.kind == HF_LAYER_AVGPOOL) continue;
+    const int64_t rows = N * L.s_out;
+    if (rows * L.out * L.in < kTcMinWork || L.out < 96 || rows < 192) continue;
+    const Tc2Choice c = tc2_estimate((int)rows, L.out, L.in, 1, 1);
     if (c.us_pair < 0.8 * c.us_single) return true;
   }
   return false;
@@ -857,16 +983,28 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   const bool images = wants_images(net, N, flags);
   if (lin) lin->a.assign(nl, nullptr), lin->delta.assign(nl, nullptr), lin->ga.assign(nl, nullptr),
       lin->ra.assign(nl, nullptr), lin->rz.assign(nl, nullptr);
+  // conv layers: the largest unfolded input (floats per sample), the position-major copy of the inputs
+  int64_t max_unfold = 0, max_unfold16 = 0;
+  for (int l = 0; l < nl; ++l)
+    if (net->L[l].unfold) {
+      max_unfold = std::max(max_unfold, (int64_t)net->L[l].s_out * pad4(net->L[l].in));
+      max_unfold16 = std::max(max_unfold16, (int64_t)net->L[l].s_out * pad8(net->L[l].in));
+    }
+  float* xn = net->L[0].kind != HF_LAYER_LINEAR ? (float*)take(sizeof(float) * N * net->L[0].s_in * pad4(net->L[0].geom.cin)) : nullptr;
+  float* ru = max_unfold ? (float*)take(sizeof(float) * N * max_unfold) : nullptr;
+  float* du = (max_unfold && !loss_only) ? (float*)take(sizeof(float) * N * max_unfold) : nullptr;
+  if (lin) lin->xn = xn, lin->ru = ru, lin->du = du, lin->U.assign(nl, nullptr);
   if (loss_only) {
-    // activations are not kept: alternate between two buffers
-    float* b0 = (float*)take(sizeof(float) * N * net->max_width);
-    float* b1 = (float*)take(sizeof(float) * N * net->max_width);
+    // activations are not kept: alternate between two buffers; unfolded inputs share one scratch matrix
+    float* b0 = (float*)take(sizeof(float) * N * net->max_act);
+    float* b1 = (float*)take(sizeof(float) * N * net->max_act);
     if (lin)
-      for (int l = 0; l < nl; ++l) lin->a[l] = (l & 1) ? b1 : b0;
+      for (int l = 0; l < nl; ++l) lin->a[l] = (l & 1) ? b1 : b0, lin->U[l] = net->L[l].unfold ? ru : nullptr;
   } else {
     for (int l = 0; l < nl; ++l) {
-      float* p = (float*)take(sizeof(float) * N * pad4(net->L[l].out));
-      if (lin) lin->a[l] = p;
+      float* p = (float*)take(sizeof(float) * N * net->L[l].s_out * pad4(net->L[l].out));
+      float* u = net->L[l].unfold ? (float*)take(sizeof(float) * N * net->L[l].s_out * pad4(net->L[l].in)) : nullptr;
+      if (lin) lin->a[l] = p, lin->U[l] = u;
     }
   }
   float* prob = nullptr;
@@ -875,24 +1013,24 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
     if (net->loss != HF_LOSS_MSE) prob = (float*)take(sizeof(float) * N * pad4(net->classes));
     dL = (float*)take(sizeof(float) * N * pad4(net->classes));
   }
-  float* b0 = loss_only ? nullptr : (float*)take(sizeof(float) * N * net->max_width);
-  float* b1 = loss_only ? nullptr : (float*)take(sizeof(float) * N * net->max_width);
+  float* b0 = loss_only ? nullptr : (float*)take(sizeof(float) * N * net->max_act);
+  float* b1 = loss_only ? nullptr : (float*)take(sizeof(float) * N * net->max_act);
   // split-K scratch: the largest weight-gradient partial set, the widest column sum
   size_t pf = 0;
   if (!loss_only)
     for (int l = net->first_trainable; l < nl; ++l) {
       const Layer& L = net->L[l];
-      if (L.w_off >= 0) pf = std::max(pf, (size_t)max_weight_splits(net, L.out, L.in, N, images) * L.out * L.in);
-      pf = std::max(pf, (size_t)colsum_plan(N) * L.out);
+      if (L.w_off >= 0) pf = std::max(pf, (size_t)max_weight_splits(net, L.out, L.in, N * L.s_out, images) * L.out * L.in);
+      pf = std::max(pf, (size_t)colsum_plan(N * L.s_out) * L.out);
     }
   float* part = pf ? (float*)take(sizeof(float) * pf) : nullptr;
   size_t pf_main = 0;
   if (!loss_only && net->L[net->first_trainable].w_off >= 0 && net->first_trainable < nl - 1) {
     const Layer& L = net->L[net->first_trainable];
-    pf_main = (size_t)max_weight_splits(net, L.out, L.in, N, images) * L.out * L.in;
+    pf_main = (size_t)max_weight_splits(net, L.out, L.in, N * L.s_out, images) * L.out * L.in;
   }
   float* part_main = pf_main ? (float*)take(sizeof(float) * pf_main) : nullptr;
-  const int fwd_max = (!loss_only && net->classes <= 32) ? 16 : 0;
+  const int fwd_max = (!loss_only && net->classes <= 32 && !net->has_conv) ? 16 : 0;
   float* pfwd = fwd_max ? (float*)take(sizeof(float) * fwd_max * N * pad4(net->classes)) : nullptr;
   if (lin) lin->partial_fwd = pfwd, lin->fwd_splits_max = fwd_max, lin->fwd_splits = 0, lin->fwd_bias = nullptr;
   if (lin) lin->wpad.assign(nl, nullptr), lin->vpad.assign(nl, nullptr);
@@ -901,6 +1039,7 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       const Layer& L = net->L[l];
       // in place needs a 16-byte row pitch AND a 16-byte aligned slice start (the flat offset of a layer depends on
       // the sizes of all layers before it: after a 30- or 250-wide layer every later slice is misaligned)
+      if (L.kind == HF_LAYER_AVGPOOL) continue;
       const bool aligned = L.w_off >= 0 ? L.w_off % 4 == 0 : (reinterpret_cast<uintptr_t>(L.w_frozen) & 15u) == 0;
       if (L.in % 4 == 0 && aligned) continue;
       float* wp = (float*)take(sizeof(float) * L.out * pad4(L.in));
@@ -910,7 +1049,7 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   // fused output head for GGN products: narrow trainable last layer without activation on top of a trainable stack
   bool head_ok = false;
   HeadPlan hp = {};
-  if (!loss_only && nl >= 2 && net->first_trainable < nl - 1) {
+  if (!loss_only && nl >= 2 && net->first_trainable < nl - 1 && !net->has_conv) {
     const Layer& Lh = net->L[nl - 1];
     head_ok = Lh.act == HF_ACT_NONE && Lh.w_off >= 0 && head_shape_ok(N, Lh.in, Lh.out, sm_count());
     if (head_ok) hp = head_plan(N, Lh.in, Lh.out, sm_count());
@@ -918,17 +1057,18 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   float* hpw = head_ok ? (float*)take(sizeof(float) * (size_t)hp.ctas * net->L[nl - 1].out * net->L[nl - 1].in) : nullptr;
   float* hpb = head_ok ? (float*)take(sizeof(float) * (size_t)hp.ctas * net->L[nl - 1].out) : nullptr;
   if (lin) lin->head_ok = head_ok, lin->head = hp, lin->head_partW = hpw, lin->head_partB = hpb;
-  const size_t col_rows = (size_t)std::max<int64_t>(std::max<int64_t>(colsum_plan(N), (N + 127) / 128), head_ok ? hp.ctas : 0);
+  const int64_t max_rows = N * net->max_s;
+  const size_t col_rows = (size_t)std::max<int64_t>(std::max<int64_t>(colsum_plan(max_rows), (max_rows + 127) / 128), head_ok ? hp.ctas : 0);
   if (lin) lin->cot.assign(nl, nullptr), lin->colbuf.assign(nl, nullptr), lin->col_rows = col_rows;
   if (!loss_only)
     for (int l = net->first_trainable; l < nl; ++l) {
       float* cb = (float*)take(sizeof(float) * col_rows * net->L[l].out);
-      float* ct = l < nl - 1 ? (float*)take(sizeof(float) * N * pad4(net->L[l].out)) : nullptr;
+      float* ct = l < nl - 1 ? (float*)take(sizeof(float) * N * net->L[l].s_out * pad4(net->L[l].out)) : nullptr;
       if (lin) lin->colbuf[l] = cb, lin->cot[l] = ct;
     }
   float* sq0 = nullptr;
   float* sq1 = nullptr;
-  if (!loss_only && net->engine == 1) {
+  if (!loss_only && net->engine == 1 && !net->has_conv) {  // (the Fisher diagonal of a convolution is not a single contraction)
     sq0 = (float*)take(sizeof(float) * N * pad4(net->max_width));
     sq1 = (float*)take(sizeof(float) * N * pad4(net->max_width));
   }
@@ -942,28 +1082,45 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
       uint16_t* hi = (uint16_t*)take(2 * plane);
       return hf_lin::ImgBuf{fp32, hi, (int64_t)(plane / 2)};
     };
-    const hf_lin::ImgBuf xi = take_img(nullptr, N, net->L[0].in);  // base = the caller's inputs, known at forward time
-    if (lin) lin->x_img = xi;
+    if (net->L[0].kind == HF_LAYER_LINEAR) {
+      const hf_lin::ImgBuf xi = take_img(nullptr, N, net->L[0].in);  // base = the caller's inputs, known at forward time
+      if (lin) lin->x_img = xi;
+    } else {
+      const hf_lin::ImgBuf xi = take_img(xn, N * net->L[0].s_in, net->L[0].geom.cin);
+      if (lin) lin->imgs.push_back(xi);
+    }
+    int64_t max_act16 = 0;  // largest image plane of any ping-pong matrix, in elements per sample
+    for (int l = 0; l < nl; ++l) max_act16 = std::max(max_act16, (int64_t)net->L[l].s_out * pad8(net->L[l].out));
     for (int l = 0; l < nl - 1; ++l) {
-      const hf_lin::ImgBuf b = take_img(lin ? lin->a[l] : nullptr, N, net->L[l].out);
+      const hf_lin::ImgBuf b = take_img(lin ? lin->a[l] : nullptr, N * net->L[l].s_out, net->L[l].out);
+      if (lin) lin->imgs.push_back(b);
+    }
+    for (int l = 0; l < nl; ++l)
+      if (net->L[l].unfold) {
+        const hf_lin::ImgBuf b = take_img(lin ? lin->U[l] : nullptr, N * net->L[l].s_out, net->L[l].in);
+        if (lin) lin->imgs.push_back(b);
+      }
+    if (ru) {
+      const hf_lin::ImgBuf b = take_img(ru, N, (int)max_unfold16);
       if (lin) lin->imgs.push_back(b);
     }
     for (int i = 0; i < 2; ++i) {
-      const hf_lin::ImgBuf b = take_img(i ? b1 : b0, N, net->max_width);
+      const hf_lin::ImgBuf b = take_img(i ? b1 : b0, N, (int)max_act16);
       if (lin) lin->imgs.push_back(b);
     }
     const hf_lin::ImgBuf dl = take_img(dL, N, net->classes);
     if (lin) lin->imgs.push_back(dl);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2 && sq0; ++i) {
       const hf_lin::ImgBuf b = take_img(i ? sq1 : sq0, N, net->max_width);
       if (lin) lin->sq_img[i] = b;
     }
     for (int l = net->first_trainable; l < nl; ++l) {
       const Layer& L = net->L[l];
       if (l < nl - 1) {
-        const hf_lin::ImgBuf b = take_img(lin ? lin->cot[l] : nullptr, N, L.out);
+        const hf_lin::ImgBuf b = take_img(lin ? lin->cot[l] : nullptr, N * L.s_out, L.out);
         if (lin) lin->imgs.push_back(b);
       }
+      if (L.kind == HF_LAYER_AVGPOOL) continue;
       const hf_lin::ImgBuf wi = take_img(nullptr, L.out, L.in);
       hf_lin::ImgBuf vi = {nullptr, nullptr, 0};
       if (L.w_off >= 0) vi = take_img(nullptr, L.out, L.in);
@@ -1004,6 +1161,8 @@ int hf_lin_create(const hf_net_t* net, int64_t batch, int32_t flags, void* d_wor
   HF_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255u) == 0, HF_ERR_WORKSPACE, "hf_lin_create: workspace must be 256-byte aligned");
   if ((flags & HF_LIN_HESSIAN) && net->L.back().act != HF_ACT_NONE)
     HF_REQUIRE(false, HF_ERR_UNSUPPORTED, "Hessian products with an activation after the last layer are not supported");
+  HF_REQUIRE(!((flags & HF_LIN_HESSIAN) && net->has_conv), HF_ERR_UNSUPPORTED,
+             "Hessian products of convolutional nets are not lowered yet (GGN products, gradient and loss are)");
   const size_t need = carve(net, batch, flags, nullptr, nullptr);
   HF_REQUIRE(workspace_bytes >= need, HF_ERR_WORKSPACE, "hf_lin_create: workspace has %zu bytes, need %zu", workspace_bytes, need);
   hf_lin* lin = new (std::nothrow) hf_lin();
@@ -1044,11 +1203,31 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
   HF_REQUIRE(d_theta || net->P == 0, HF_ERR_INVALID, "hf_lin_forward: theta is null");
   const int nl = (int)net->L.size();
   lin->x = d_x, lin->n_total = n_total;
+  if (net->L[0].kind != HF_LAYER_LINEAR) {  // inputs arrive NCHW: position-major copy (+ image) for the tile engines
+    const Layer& L0 = net->L[0];
+    nchw_to_nhwc_kernel<<<conv_blocks(lin->N * L0.s_in * (int64_t)L0.geom.cin), 256, 0, stream>>>(
+        d_x, lin->xn, lin->N, L0.geom.cin, L0.s_in, pad4(L0.geom.cin), image_for(lin, lin->xn, L0.geom.cin));
+    HF_LAUNCH_CHECK();
+  }
   for (int l = 0; l < nl; ++l) {
     const Layer& L = net->L[l];
+    if (L.kind == HF_LAYER_AVGPOOL) {
+      avgpool_kernel<<<conv_blocks(lin->N * (int64_t)L.out), 256, 0, stream>>>(lin->a[l - 1], pad4(L.out), lin->a[l], lin->N, L.s_in, L.out,
+                                                                                Image16{nullptr, 0, 0}, nullptr);
+      HF_LAUNCH_CHECK();
+      continue;
+    }
+    if (L.unfold) {  // the unfolded input (+ its image) stays resident: every product of the solve contracts with it
+      const float* src = l == 0 ? lin->xn : lin->a[l - 1];
+      im2col_kernel<<<conv_blocks(rows_out(lin, l) * L.geom.cin), 256, 0, stream>>>(src, pad4(L.geom.cin), lin->U[l], pad4(L.in), lin->N, L.geom,
+                                                                                   image_for(lin, lin->U[l], L.in), nullptr);
+      HF_LAUNCH_CHECK();
+    }
+    int ld_in = 0;
+    const float* a_in = layer_input(lin, l, &ld_in);
     GemmArgs g = blank_gemm();
-    g.M = (int)lin->N, g.N = L.out, g.K = L.in, g.n_pairs = 1;
-    g.A[0] = op_kc(l == 0 ? d_x : lin->a[l - 1], l == 0 ? L.in : pad4(L.in));
+    g.M = (int)rows_out(lin, l), g.N = L.out, g.K = L.in, g.n_pairs = 1;
+    g.A[0] = op_kc(a_in, ld_in);
     g.B[0] = op_kc(weight_ptr(L, d_theta), L.in);
     g.C = lin->a[l], g.ldc = pad4(L.out);
     g.epi = EPI_BIAS_ACT, g.act = L.act, g.bias = bias_ptr(L, d_theta);
@@ -1078,13 +1257,17 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     const Image16 none = {nullptr, 0, 0};
     int rc = HF_OK;
     if (lin->use_images) {
-      lin->x_img.base = d_x;
-      rc = push(SplitSegment{d_x, lin->N, net->L[0].in, net->L[0].in, nullptr, 0, image_for(lin, d_x, net->L[0].in)});
+      if (net->L[0].kind == HF_LAYER_LINEAR) {
+        lin->x_img.base = d_x;
+        rc = push(SplitSegment{d_x, lin->N, net->L[0].in, net->L[0].in, nullptr, 0, image_for(lin, d_x, net->L[0].in)});
+      }
       for (int l = 0; l < nl - 1 && !rc; ++l)
-        rc = push(SplitSegment{lin->a[l], lin->N, net->L[l].out, pad4(net->L[l].out), nullptr, 0, image_for(lin, lin->a[l], net->L[l].out)});
+        rc = push(SplitSegment{lin->a[l], rows_out(lin, l), net->L[l].out, pad4(net->L[l].out), nullptr, 0,
+                               image_for(lin, lin->a[l], net->L[l].out)});
     }
     for (int l = net->first_trainable; l < nl && !rc && !(lin->flags & HF_LIN_LOSS_ONLY); ++l) {
       const Layer& L = net->L[l];
+      if (L.kind == HF_LAYER_AVGPOOL) continue;
       const bool img = lin->use_images && lin->w_img[l].hi;
       if (!lin->wpad[l] && !img) continue;
       if (img) lin->w_img[l].base = lin->wpad[l] ? lin->wpad[l] : weight_ptr(L, d_theta);
@@ -1210,6 +1393,9 @@ int hf_hessian_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, flo
 int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t accumulate, void* stream) {
   int rc = check_ready(lin, "hf_fisher_diag", false);
   if (rc) return rc;
+  // for a convolution the square sits outside the sum over positions: (d^2)^T (a^2) is NOT the diagonal (SURVEY.md
+  // section 7, hard part 7); per-sample weight-gradient tiles are the next step
+  HF_REQUIRE(!lin->net->has_conv, HF_ERR_UNSUPPORTED, "the empirical-Fisher diagonal of convolutional nets is not lowered yet");
   HF_REQUIRE(d_out, HF_ERR_INVALID, "hf_fisher_diag: null output");
   return backward_sweep(lin, d_theta, nullptr, lin->deltaL, d_out, accumulate, BACK_FISHER, nullptr,
                         (cudaStream_t)stream);

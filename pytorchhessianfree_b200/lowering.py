@@ -48,10 +48,14 @@ def flat_offsets(params_list):
 
 def _unsupported(what):
     raise NotImplementedError(
-        f"{what} cannot be lowered to the sm_100a layer program (supported: Linear, ReLU, Sigmoid, Tanh, Flatten, "
-        "Identity, eval-mode Dropout; MSELoss, CrossEntropyLoss, BCEWithLogitsLoss). Pass your own `mvp` to "
-        "`step`, or restructure the model."
+        f"{what} cannot be lowered to the sm_100a layer program (supported: Linear, Conv2d, ReLU, Sigmoid, Tanh, a "
+        "global AvgPool2d / AdaptiveAvgPool2d(1), Flatten, Identity, eval-mode Dropout; MSELoss, CrossEntropyLoss, "
+        "BCEWithLogitsLoss). Pass your own `mvp` to `step`, or restructure the model."
     )
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
 
 
 def lower_loss(loss_func):
@@ -95,13 +99,60 @@ def _check_param_use(layers, offsets):
     return set(used)
 
 
-def lower_module(model, loss_func, params_list):
-    """Walk a (nested) ``nn.Sequential`` of Linear/activation layers."""
+def lower_module(model, loss_func, params_list, input_shape=None):
+    """Walk a (nested) ``nn.Sequential`` of Linear / Conv2d / activation / pooling layers.
+
+    ``input_shape`` = (channels, height, width) of one sample is needed when the model starts with a convolution (the
+    entry points that call this pass the shape of the data they were given)."""
     offsets, n_params = flat_offsets(params_list)
     kind, reduction = lower_loss(loss_func)
     layers: List[LayerSpec] = []
+    fmap = tuple(input_shape) if input_shape is not None and len(input_shape) == 3 else None  # (c, h, w) of the running feature map
     for m in _leaves(model):
-        if isinstance(m, nn.Linear):
+        if isinstance(m, nn.Conv2d):
+            if fmap is None:
+                _unsupported("a Conv2d whose input feature-map size is unknown (inputs must be [batch, c, h, w])" if not layers
+                             else "a Conv2d after a fully connected layer")
+            if (m.groups != 1 or _pair(m.dilation) != (1, 1) or m.padding_mode != "zeros" or isinstance(m.padding, str)
+                    or len(set(_pair(m.stride))) != 1 or len(set(_pair(m.padding))) != 1):
+                _unsupported("a Conv2d with groups, dilation, string/non-zero-mode padding or anisotropic stride/padding")
+            c, h, w_ = fmap
+            if c != m.in_channels:
+                raise ValueError(f"Conv2d expects {m.in_channels} input channels, the feature map has {c}")
+            kh, kw = _pair(m.kernel_size)
+            st, pd = _pair(m.stride)[0], _pair(m.padding)[0]
+            ho, wo = (h + 2 * pd - kh) // st + 1, (w_ + 2 * pd - kw) // st + 1
+            w, b = m.weight, m.bias
+            spec = LayerSpec(c * kh * kw, m.out_channels, "none", b is not None, kind="conv2d",
+                             geom=(c, h, w_, kh, kw, st, pd, ho, wo))
+            fmap = (m.out_channels, ho, wo)
+            for prm, off_name, frozen_name in ((w, "w_offset", "w_frozen"), (b, "b_offset", "b_frozen")):
+                if prm is None:
+                    continue
+                if prm.requires_grad:
+                    if id(prm) not in offsets:
+                        raise ValueError("a trainable model parameter is not among the optimizer's parameters")
+                    setattr(spec, off_name, offsets[id(prm)])
+                else:
+                    setattr(spec, frozen_name, prm.detach().reshape(m.out_channels, -1))
+            layers.append(spec)
+        elif isinstance(m, (nn.AvgPool2d, nn.AdaptiveAvgPool2d)):
+            if fmap is None:
+                _unsupported("a pooling layer outside a convolutional stack")
+            c, h, w_ = fmap
+            if isinstance(m, nn.AdaptiveAvgPool2d):
+                whole = _pair(m.output_size) == (1, 1)
+            else:
+                whole = (_pair(m.kernel_size) == (h, w_) and _pair(m.padding) == (0, 0)
+                         and (m.stride is None or _pair(m.stride) == (h, w_) or (h, w_) == _pair(m.kernel_size)))
+            if not whole:
+                _unsupported("an average pool that does not cover the whole feature map")
+            layers.append(LayerSpec(c, c, "none", False, kind="avgpool", geom=(c, h, w_, 0, 0, 0, 0, 1, 1)))
+            fmap = (c, 1, 1)
+        elif isinstance(m, nn.Linear):
+            if fmap is not None and fmap[1:] != (1, 1):
+                _unsupported("a Linear layer on a feature map larger than 1x1 (pool first)")
+            fmap = None
             w, b = m.weight, m.bias
             spec = LayerSpec(m.in_features, m.out_features, "none", b is not None)
             for prm, off_name, frozen_name in ((w, "w_offset", "w_frozen"), (b, "b_offset", "b_frozen")):
@@ -115,19 +166,21 @@ def lower_module(model, loss_func, params_list):
                     setattr(spec, frozen_name, prm.detach())
             layers.append(spec)
         elif type(m) in _ACT_MODULES:
-            if not layers or layers[-1].act != "none":
-                _unsupported("an activation that does not directly follow a Linear layer")
+            if not layers or layers[-1].act != "none" or layers[-1].kind == "avgpool":
+                _unsupported("an activation that does not directly follow a Linear or Conv2d layer")
             layers[-1].act = _ACT_MODULES[type(m)]
         elif isinstance(m, (nn.Identity, nn.Flatten)):
-            if isinstance(m, nn.Flatten) and layers:
-                _unsupported("Flatten after the first Linear layer")
+            if isinstance(m, nn.Flatten) and layers and not (fmap is not None and fmap[1:] == (1, 1)):
+                _unsupported("Flatten after the first layer (other than of a 1x1 feature map)")
         elif isinstance(m, nn.Dropout):
             if m.training and m.p > 0:
                 _unsupported("train-mode Dropout (non-deterministic curvature products)")
         else:
             _unsupported(f"module {type(m).__name__}")
     if not layers:
-        _unsupported("a model without Linear layers")
+        _unsupported("a model without Linear or Conv2d layers")
+    if fmap is not None and fmap[1:] != (1, 1):
+        _unsupported("a convolutional net whose output is a feature map (end with a global average pool)")
     if _check_param_use(layers, offsets) != set(offsets.values()):
         raise ValueError("the optimizer holds trainable parameters that the model does not use")
     return Program(layers, kind, reduction, n_params)

@@ -28,10 +28,14 @@ class LayerSpec:
     b_offset: int = -1
     w_frozen: Optional[torch.Tensor] = None
     b_frozen: Optional[torch.Tensor] = None
+    # "conv2d": in_features = c_in*k_h*k_w and geom = (c_in, h_in, w_in, k_h, k_w, stride, pad, h_out, w_out);
+    # "avgpool": average over the whole (h_in, w_in) map, geom = (c, h_in, w_in, 0, 0, 0, 0, 1, 1), no parameters
+    kind: str = "linear"
+    geom: tuple = ()
 
     def signature(self):
         return (self.in_features, self.out_features, self.act, self.has_bias, self.w_offset, self.b_offset,
-                _lib.ptr(self.w_frozen), _lib.ptr(self.b_frozen))
+                _lib.ptr(self.w_frozen), _lib.ptr(self.b_frozen), self.kind, tuple(self.geom))
 
 
 ENGINES = {"simt": 0, "tc": 1}
@@ -52,6 +56,9 @@ class NativeNet:
         for d, l in zip(arr, layers):
             d.in_features, d.out_features, d.act, d.has_bias = l.in_features, l.out_features, ACT[l.act], int(l.has_bias)
             d.w_offset, d.b_offset = l.w_offset, l.b_offset if l.has_bias else -1
+            d.kind = _lib.LAYER_KIND[l.kind]
+            if l.kind != "linear":
+                (d.c_in, d.h_in, d.w_in, d.k_h, d.k_w, d.stride, d.pad, d.h_out, d.w_out) = l.geom
             for name, t in (("d_w_frozen", l.w_frozen), ("d_b_frozen", l.b_frozen)):
                 if t is not None:
                     _lib.require_cuda(t, "frozen parameter")
@@ -64,6 +71,8 @@ class NativeNet:
         self.engine = engine
         _lib.check(self.lib.hf_net_set_engine(self.handle, ENGINES[engine]))
         self.in_features, self.classes = layers[0].in_features, layers[-1].out_features
+        # a convolution first: inputs are [batch, c_in, h_in, w_in] (NCHW, as the user's model takes them)
+        self.input_shape = tuple(layers[0].geom[:3]) if layers[0].kind != "linear" else None
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -91,10 +100,14 @@ class Linearization:
         _lib.require_cuda(targets, "targets")
         self.net, self.lib = net, net.lib
         x = x.detach()
-        if x.dim() != 2:
-            x = x.reshape(x.shape[0], -1)
-        if x.shape[1] != net.in_features:
-            raise ValueError(f"inputs have {x.shape[1]} features, the first layer takes {net.in_features}")
+        if net.input_shape is not None:
+            if tuple(x.shape[1:]) != net.input_shape:
+                raise ValueError(f"inputs have shape {tuple(x.shape[1:])}, the first convolution takes {net.input_shape}")
+        else:
+            if x.dim() != 2:
+                x = x.reshape(x.shape[0], -1)
+            if x.shape[1] != net.in_features:
+                raise ValueError(f"inputs have {x.shape[1]} features, the first layer takes {net.in_features}")
         self.x = x.to(torch.float32).contiguous()
         self.n = int(x.shape[0])
         t = targets.detach()

@@ -37,6 +37,12 @@ from .problem import NativeProblem
 from .utils import vector_to_trainparams
 
 
+def _sample_shape(datalist):
+    """(c, h, w) of one sample when the chunks hold image batches [n, c, h, w] (a convolution comes first), else None."""
+    x = datalist[0][0]
+    return tuple(x.shape[1:]) if x.dim() == 4 else None
+
+
 class HessianFree(torch.optim.Optimizer):
     """Hessian-free optimizer (Martens 2010; Martens & Sutskever 2012)."""
 
@@ -352,7 +358,7 @@ class HessianFree(torch.optim.Optimizer):
         shard of the global lists; sums run over all ranks."""
         if reduction not in ["mean", "sum"]:
             raise ValueError(f"Invalid reduction {reduction}")
-        prog = lower_module(model, loss_func, self._params_list)
+        prog = lower_module(model, loss_func, self._params_list, input_shape=_sample_shape(mvp_datalist or loss_datalist))
         if prog.reduction != reduction:
             raise ValueError(f"the loss function reduces by {prog.reduction!r} but reduction={reduction!r} was given "
                              "(check with `test_reduction`)")
@@ -392,7 +398,7 @@ class HessianFree(torch.optim.Optimizer):
         if reduction not in ["mean", "sum"]:
             raise ValueError(f"Invalid reduction {reduction}")
         assert len(datalist) > 1, "This test is only meaningful for a data list with at least two entries."
-        prog = lower_module(model, loss_func, self._params_list)
+        prog = lower_module(model, loss_func, self._params_list, input_shape=_sample_shape(datalist))
         theta = self._flat_params()
         net = self._net_for(prog)
         curv = self._group["curvature_opt"]
@@ -431,7 +437,7 @@ class HessianFree(torch.optim.Optimizer):
         (reference ``optimizer.py:928-952``).  Unlike the reference, the preconditioner is returned."""
         if reduction not in ["sum", "mean"]:
             raise ValueError(f"reduction {reduction} is not supported.")
-        prog = lower_module(model, loss_func, self._params_list)
+        prog = lower_module(model, loss_func, self._params_list, input_shape=_sample_shape([(inputs, targets)]))
         if prog.reduction != reduction:
             raise ValueError(f"the loss function reduces by {prog.reduction!r} but reduction={reduction!r} was given")
         theta = self._flat_params()

@@ -17,7 +17,7 @@ def _diag_EF(model, loss_function, inputs, targets, reduction, engine="simt"):
     if reduction not in ["sum", "mean"]:
         raise ValueError(f"reduction {reduction} is not supported.")
     params = [p for p in model.parameters() if p.requires_grad]
-    prog = lower_module(model, loss_function, params)
+    prog = lower_module(model, loss_function, params, input_shape=tuple(inputs.shape[1:]) if inputs.dim() == 4 else None)
     if prog.reduction != reduction:
         raise ValueError(f"the loss function reduces by {prog.reduction!r} but reduction={reduction!r} was given")
     _lib.require_cuda(inputs, "inputs")

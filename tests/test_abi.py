@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_no_compute_entry_points_need_a_gpu_to_load():
     lib = _lib.load()
-    assert lib.hf_abi_version() == 1
+    assert lib.hf_abi_version() == 2
     assert lib.hf_pcg_state_bytes(250) > 250 * 8
     assert lib.hf_pcg_m_iters_offset() % 8 == 0
     assert ctypes.sizeof(_lib.PcgStatus) == 80 and ctypes.sizeof(_lib.LayerDesc) == 48

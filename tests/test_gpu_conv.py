@@ -1,0 +1,160 @@
+"""GPU: the first convolutional slice (reference examples/run_allcnnc_cifar100_deepobs.py,
+eval mode): Conv2d / ReLU / global average pool / Linear nets lowered to the layer program -- loss, gradient and GGN
+products against the CPU oracle (autograd on the same module), chunked == full batch, optimizer steps against the
+oracle's, and loud refusals for what is not lowered yet (Hessian products, Fisher diagonal of conv nets)."""
+import copy
+import warnings
+
+import pytest
+import torch
+from torch import nn
+
+import hf_oracle as O
+
+from pytorchhessianfree_b200 import HessianFree
+from pytorchhessianfree_b200.lowering import lower_module
+from pytorchhessianfree_b200.native import NativeNet
+from pytorchhessianfree_b200.problem import NativeProblem
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def small_cnn(act=nn.ReLU):
+    # stride 2, 'same' and 'valid' 3x3, a 1x1 convolution, bias on and off, global average pool: the shapes of All-CNN-C in small
+    return nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), act(), nn.Conv2d(8, 8, 3, stride=2, padding=1, bias=False), act(),
+                         nn.Conv2d(8, 16, 3), act(), nn.Conv2d(16, 10, 1), act(), nn.AvgPool2d(4), nn.Flatten())
+
+
+def cnn_with_head():
+    return nn.Sequential(nn.Conv2d(2, 6, 3, padding=1), nn.Sigmoid(), nn.Conv2d(6, 12, 5, stride=2, padding=2), nn.Sigmoid(),
+                         nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(12, 7), nn.Tanh(), nn.Linear(7, 5))
+
+
+def allcnnc(classes=100):
+    """All-CNN-C (Springenberg et al.; the DeepOBS cifar100_allcnnc architecture with symmetric padding), eval mode."""
+    def block(cin, cout, k, stride=1, pad=0):
+        return [nn.Conv2d(cin, cout, k, stride=stride, padding=pad), nn.ReLU()]
+    layers = (block(3, 96, 3, pad=1) + block(96, 96, 3, pad=1) + block(96, 96, 3, stride=2, pad=1) + block(96, 192, 3, pad=1)
+              + block(192, 192, 3, pad=1) + block(192, 192, 3, stride=2, pad=1) + block(192, 192, 3) + block(192, 192, 1)
+              + block(192, classes, 1) + [nn.AvgPool2d(6), nn.Flatten()])
+    return nn.Sequential(*layers)
+
+
+def errs(got, want):
+    got, want = got.double().cpu(), want.double()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item(), ((got - want).norm() / want.norm().clamp_min(1e-30)).item()
+
+
+def device_problem(model, loss_fn, chunks, engine, curv="ggn"):
+    m = copy.deepcopy(model).to(DEV)
+    params = [p for p in m.parameters() if p.requires_grad]
+    prog = lower_module(m, loss_fn, params, input_shape=tuple(chunks[0][0].shape[1:]))
+    theta = torch.cat([p.detach().reshape(-1) for p in params])
+    net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine)
+    return NativeProblem(net, theta, curv, [(x.to(DEV), t.to(DEV)) for x, t in chunks])
+
+
+CASES = {
+    "small_cnn_ce": (small_cnn, nn.CrossEntropyLoss, (3, 12, 12), 10, "ce"),
+    "small_cnn_tanh_mse": (lambda: small_cnn(nn.Tanh), nn.MSELoss, (3, 12, 12), 10, "mse"),
+    "cnn_head_bce": (cnn_with_head, nn.BCEWithLogitsLoss, (2, 9, 9), 5, "bce"),
+}
+
+
+def make_case(name, n, seed):
+    build, loss_cls, shape, classes, kind = CASES[name]
+    torch.manual_seed(seed)
+    model = build()
+    g = torch.Generator().manual_seed(100 + seed)
+    x = torch.rand(n, *shape, generator=g)
+    t = torch.randint(0, classes, (n,), generator=g) if kind == "ce" else torch.rand(n, classes, generator=g)
+    return model, loss_cls(), x, t
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+@pytest.mark.parametrize("n", [1, 6, 37])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_conv_products_match_oracle(name, n, engine):
+    for seed in (0, 1, 42):
+        model, loss_fn, x, t = make_case(name, n, seed)
+        params = list(model.parameters())
+        out = model(x)
+        loss = loss_fn(out, t)
+        v = torch.randn(sum(p.numel() for p in params))
+        want_g = O.flatten(torch.autograd.grad(loss, params, retain_graph=True))
+        want_G = O.Gv(loss, out, params, v)
+        prob = device_problem(model, loss_fn, [(x, t)], engine)
+        got_loss = float(prob.linearize().item())
+        assert abs(got_loss - float(loss)) <= 1e-5 * abs(float(loss))
+        e_g, e_G = errs(prob.gradient(), want_g), errs(prob.mvp(v.to(DEV)), want_G)
+        assert max(e_g) < 1e-4, f"gradient: max {e_g[0]:.1e} l2 {e_g[1]:.1e}"
+        assert max(e_G) < 1e-4, f"GGN product: max {e_G[0]:.1e} l2 {e_G[1]:.1e}"
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_conv_chunked_equals_full_batch(name):
+    model, loss_fn, x, t = make_case(name, 23, 3)
+    full = device_problem(model, loss_fn, [(x, t)], "tc")
+    parts = device_problem(model, loss_fn, [(x[:7], t[:7]), (x[7:8], t[7:8]), (x[8:], t[8:])], "tc")
+    v = torch.randn_like(full.theta)
+    assert abs(full.linearize().item() - parts.linearize().item()) <= 1e-6 * abs(full.linearize().item())
+    for a, b in ((full.gradient(), parts.gradient()), (full.mvp(v), parts.mvp(v))):
+        assert max(errs(b, a.cpu())) < 2e-5
+
+
+def test_allcnnc_ggn_product_at_batch_64():
+    """BASELINE.json configs[4]'s architecture at the size BASELINE.md quotes the CPU time for (N = 64, 537 ms per
+    reference `_Gv`): gradient and GGN product of the tensor-core path against the CPU oracle, rtol 1e-4."""
+    torch.manual_seed(0)
+    model = allcnnc()
+    loss_fn = nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(7)
+    x, t = torch.rand(64, 3, 32, 32, generator=g), torch.randint(0, 100, (64,), generator=g)
+    params = list(model.parameters())
+    assert sum(p.numel() for p in params) == 1387108  # P of configs[4]
+    out = model(x)
+    loss = loss_fn(out, t)
+    v = torch.randn(1387108, generator=g)
+    want_g = O.flatten(torch.autograd.grad(loss, params, retain_graph=True))
+    want_G = O.Gv(loss, out, params, v)
+    prob = device_problem(model, loss_fn, [(x, t)], "tc")
+    assert abs(prob.linearize().item() - float(loss)) <= 1e-5 * float(loss)
+    e_g, e_G = errs(prob.gradient(), want_g), errs(prob.mvp(v.to(DEV)), want_G)
+    print(f"\nAll-CNN-C N=64: gradient max {e_g[0]:.1e} l2 {e_g[1]:.1e}; GGN product max {e_G[0]:.1e} l2 {e_G[1]:.1e}")
+    assert max(e_g) < 1e-4 and max(e_G) < 1e-4
+    # symmetric, positive semi-definite
+    w = torch.randn_like(v)
+    Bv, Bw = prob.mvp(v.to(DEV)), prob.mvp(w.to(DEV))
+    a, b = torch.dot(w.to(DEV).double(), Bv.double()).item(), torch.dot(v.to(DEV).double(), Bw.double()).item()
+    assert abs(a - b) <= 1e-4 * max(abs(a), abs(b)) and torch.dot(v.to(DEV).double(), Bv.double()).item() >= 0.0
+
+
+def test_acc_step_on_a_conv_net_follows_the_oracle():
+    model, loss_fn, x, t = make_case("small_cnn_ce", 24, 5)
+    ref_model = copy.deepcopy(model)
+    model = model.to(DEV)
+    opt = HessianFree(model.parameters(), cg_max_iter=15)
+    orc = O.OracleHF(ref_model.parameters(), cg_max_iter=15)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for step in range(3):
+            chunks = [(x[:10], t[:10]), (x[10:], t[10:])]
+            opt.acc_step(model, loss_fn, [(a.to(DEV), b.to(DEV)) for a, b in chunks], reduction="mean")
+            orc.acc_step(ref_model, loss_fn, chunks, reduction="mean")
+            assert opt.state["init_losses"][-1] == pytest.approx(orc.log["init_losses"][-1], rel=1e-4)
+    for p, q in zip(model.parameters(), ref_model.parameters()):
+        assert torch.allclose(p.data.cpu(), q.data, atol=1e-4)
+
+
+def test_unlowered_conv_features_are_refused_loudly():
+    model, loss_fn, x, t = make_case("small_cnn_ce", 4, 0)
+    with pytest.raises(NotImplementedError, match="Hessian"):
+        device_problem(model, loss_fn, [(x, t)], "tc", curv="hessian")
+    m = copy.deepcopy(model).to(DEV)
+    opt = HessianFree(m.parameters())
+    with pytest.raises(NotImplementedError, match="Fisher"):
+        opt.get_preconditioner(m, loss_fn, x.to(DEV), t.to(DEV), "mean")
+    with pytest.raises(NotImplementedError):
+        lower_module(nn.Sequential(nn.Conv2d(3, 4, 3, groups=1, dilation=2), nn.AdaptiveAvgPool2d(1), nn.Flatten()), loss_fn,
+                     [], input_shape=(3, 8, 8))
