@@ -21,10 +21,13 @@ void note_launch();
   } while (0)
 
 // every kernel launch goes through one of these two, so hf_debug_launch_count() is exact
-#define HF_LAUNCH_CHECK()            \
-  do {                               \
-    ::hf::note_launch();             \
-    HF_CUDA(cudaGetLastError());     \
+#define HF_STR2(x) #x
+#define HF_STR(x) HF_STR2(x)
+#define HF_LAUNCH_CHECK()                                                                          \
+  do {                                                                                             \
+    ::hf::note_launch();                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess) return ::hf::cuda_fail(e__, "kernel launch at " __FILE__ ":" HF_STR(__LINE__)); \
   } while (0)
 
 #define HF_REQUIRE(cond, code, ...)  \

@@ -1068,7 +1068,8 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
     }
   float* sq0 = nullptr;
   float* sq1 = nullptr;
-  if (!loss_only && net->engine == 1 && !net->has_conv) {  // (the Fisher diagonal of a convolution is not a single contraction)
+  const bool have_sq = !loss_only && net->engine == 1 && !net->has_conv;  // (the Fisher diagonal of a convolution is not a single contraction)
+  if (have_sq) {
     sq0 = (float*)take(sizeof(float) * N * pad4(net->max_width));
     sq1 = (float*)take(sizeof(float) * N * pad4(net->max_width));
   }
@@ -1100,7 +1101,7 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
         const hf_lin::ImgBuf b = take_img(lin ? lin->U[l] : nullptr, N * net->L[l].s_out, net->L[l].in);
         if (lin) lin->imgs.push_back(b);
       }
-    if (ru) {
+    if (max_unfold) {  // (decided by sizes, never by pointers: the measuring pass of this function has none)
       const hf_lin::ImgBuf b = take_img(ru, N, (int)max_unfold16);
       if (lin) lin->imgs.push_back(b);
     }
@@ -1110,7 +1111,7 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
     }
     const hf_lin::ImgBuf dl = take_img(dL, N, net->classes);
     if (lin) lin->imgs.push_back(dl);
-    for (int i = 0; i < 2 && sq0; ++i) {
+    for (int i = 0; i < 2 && have_sq; ++i) {
       const hf_lin::ImgBuf b = take_img(i ? sq1 : sq0, N, net->max_width);
       if (lin) lin->sq_img[i] = b;
     }

@@ -31,7 +31,7 @@ def test_no_compute_entry_points_need_a_gpu_to_load():
     assert lib.hf_abi_version() == 2
     assert lib.hf_pcg_state_bytes(250) > 250 * 8
     assert lib.hf_pcg_m_iters_offset() % 8 == 0
-    assert ctypes.sizeof(_lib.PcgStatus) == 80 and ctypes.sizeof(_lib.LayerDesc) == 48
+    assert ctypes.sizeof(_lib.PcgStatus) == 80 and ctypes.sizeof(_lib.LayerDesc) == 88
 
 
 def test_product_code_never_touches_the_oracle():

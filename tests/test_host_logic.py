@@ -164,3 +164,24 @@ def test_untransposed_matmul_is_refused():
     out = x @ W
     with pytest.raises(NotImplementedError, match="weight.t"):
         lower_graph(nn.MSELoss()(out, torch.rand(3, 4)), out, [W])
+
+
+def test_conv_lowering_geometry():
+    """nn.Conv2d / global average pool -> layer program: the unfolded width c_in*k_h*k_w, the output map, flat offsets."""
+    model = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(), nn.Conv2d(8, 6, 3, stride=2, padding=1, bias=False), nn.ReLU(),
+                          nn.AvgPool2d(6), nn.Flatten(), nn.Linear(6, 4))
+    prog = lower_module(model, nn.CrossEntropyLoss(), list(model.parameters()), input_shape=(3, 12, 12))
+    kinds = [(l.kind, l.in_features, l.out_features, l.act, l.has_bias) for l in prog.layers]
+    assert kinds == [("conv2d", 27, 8, "relu", True), ("conv2d", 72, 6, "relu", False), ("avgpool", 6, 6, "none", False),
+                     ("linear", 6, 4, "none", True)]
+    assert prog.layers[0].geom == (3, 12, 12, 3, 3, 1, 1, 12, 12) and prog.layers[1].geom == (8, 12, 12, 3, 3, 2, 1, 6, 6)
+    assert [l.w_offset for l in prog.layers] == [0, 224, -1, 656] and prog.n_params == 656 + 24 + 4
+    bad = nn.Sequential(nn.Conv2d(3, 8, 3), nn.AvgPool2d(2), nn.Flatten())
+    with pytest.raises(NotImplementedError, match="whole feature map"):
+        lower_module(bad, nn.MSELoss(), list(bad.parameters()), input_shape=(3, 12, 12))
+    bad = nn.Sequential(nn.Conv2d(3, 8, 3), nn.AdaptiveAvgPool2d(1), nn.Flatten())
+    with pytest.raises(NotImplementedError, match="feature-map size is unknown"):
+        lower_module(bad, nn.MSELoss(), list(bad.parameters()))
+    bad = nn.Sequential(nn.Conv2d(3, 8, 3), nn.ReLU())
+    with pytest.raises(NotImplementedError, match="global average pool"):
+        lower_module(bad, nn.MSELoss(), list(bad.parameters()), input_shape=(3, 12, 12))
