@@ -259,6 +259,58 @@ def lower_graph(loss, outputs, params_list):
             if node is None:
                 _unsupported("an activation applied to a constant")
             continue
+        if nm in ("ViewBackward0", "ReshapeAliasBackward0", "UnsafeViewBackward0"):
+            # flatten of a pooled [batch, c, 1, 1] map (or a no-op view): same numbers, same order
+            sizes = tuple(node._saved_self_sym_sizes)
+            if len(sizes) == 4 and sizes[2:] != (1, 1):
+                _unsupported("flattening a feature map larger than 1x1 (pool first)")
+            node = node.next_functions[0][0]
+            if node is None:
+                _unsupported("a view of a constant")
+            continue
+        if nm in ("AvgPool2DBackward0", "MeanBackward1"):
+            if pending_act != "none":
+                _unsupported("an activation directly after an average pool")
+            if nm == "AvgPool2DBackward0":
+                c, h, w_ = tuple(node._saved_self.shape[1:])
+                whole = (tuple(node._saved_kernel_size) == (h, w_) and tuple(node._saved_padding) == (0, 0)
+                         and node._saved_divisor_override is None)
+            else:
+                c, h, w_ = tuple(node._saved_self_sym_sizes)[1:]
+                dims = sorted(d % 4 for d in node._saved_dim)
+                whole = dims == [2, 3]
+            if not whole:
+                _unsupported("an average pool that does not cover the whole feature map")
+            rev.append(LayerSpec(c, c, "none", False, kind="avgpool", geom=(c, h, w_, 0, 0, 0, 0, 1, 1)))
+            node = node.next_functions[0][0]
+            if node is None:
+                _unsupported("a pool applied to a constant")
+            continue
+        if nm == "ConvolutionBackward0":
+            if (node._saved_transposed or node._saved_groups != 1 or tuple(node._saved_dilation) != (1, 1)
+                    or len(set(node._saved_stride)) != 1 or len(set(node._saved_padding)) != 1 or len(node._saved_stride) != 2):
+                _unsupported("a convolution with groups, dilation, transposition or anisotropic stride/padding")
+            nxt = node.next_functions[0][0]
+            weight = _leaf_param(node.next_functions[1][0], False)
+            bias = _leaf_param(node.next_functions[2][0], False) if len(node.next_functions) > 2 else None
+            has_bias = node._saved_bias_sym_sizes_opt is not None and tuple(node._saved_bias_sym_sizes_opt) not in ((), (0,))
+            if weight is None or (has_bias and bias is None):
+                _unsupported("a convolution with frozen parameters inside the differentiated part of the graph")
+            if id(weight) not in offsets or (bias is not None and id(bias) not in offsets):
+                raise ValueError("the graph uses a trainable parameter that is not among the optimizer's parameters")
+            saved_in = node._saved_input
+            c, h, w_ = tuple(saved_in.shape[1:])
+            cout, _, kh, kw = tuple(weight.shape)
+            st, pd = int(node._saved_stride[0]), int(node._saved_padding[0])
+            ho, wo = (h + 2 * pd - kh) // st + 1, (w_ + 2 * pd - kw) // st + 1
+            rev.append(LayerSpec(c * kh * kw, cout, pending_act, bias is not None, offsets[id(weight)],
+                                 offsets[id(bias)] if bias is not None else -1, kind="conv2d",
+                                 geom=(c, h, w_, kh, kw, st, pd, ho, wo)))
+            pending_act = "none"
+            if nxt is None:
+                inputs = saved_in
+            node = nxt
+            continue
         if nm == "AddmmBackward0":
             if float(node._saved_alpha) != 1.0 or float(node._saved_beta) != 1.0:
                 _unsupported("addmm with alpha/beta != 1")
@@ -284,12 +336,15 @@ def lower_graph(loss, outputs, params_list):
             inputs = saved_in
         node = nxt
     if pending_act != "none" or not rev or inputs is None:
-        _unsupported("a graph that does not end in a Linear layer fed by constant inputs")
+        _unsupported("a graph that does not end in a Linear or Conv2d layer fed by constant inputs")
     layers = rev[::-1]
     if _check_param_use(layers, offsets) != set(offsets.values()):
         raise ValueError("One of the optimizer's trainable parameters is not used in the graph of `loss`")
-    if inputs.dim() != 2:
-        _unsupported("Linear layers applied to inputs that are not [batch, features]")
+    if inputs.dim() != (2 if layers[0].kind == "linear" else 4):
+        _unsupported("layers applied to inputs that are neither [batch, features] nor [batch, c, h, w]")
+    for below, above in zip(layers, layers[1:]):
+        if above.kind == "linear" and below.kind == "conv2d" and below.geom[7:] != (1, 1):
+            _unsupported("a Linear layer on a feature map larger than 1x1 (pool first)")
     if kind != "ce" and out_val is not None and tuple(targets.shape) != tuple(out_val.shape):
         _unsupported("a loss with broadcast targets")
     return Program(layers, kind, reduction, n_params, inputs=inputs, targets=targets)

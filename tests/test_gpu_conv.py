@@ -147,6 +147,30 @@ def test_acc_step_on_a_conv_net_follows_the_oracle():
         assert torch.allclose(p.data.cpu(), q.data, atol=1e-4)
 
 
+def test_step_and_static_products_through_the_autograd_graph():
+    """`step(forward)` and the static `_Gv` only see an autograd graph (reference optimizer.py:137-151, :457-462): the
+    conv layer program is recovered from ConvolutionBackward0 / AvgPool2DBackward0 / ViewBackward0 nodes."""
+    model, loss_fn, x, t = make_case("small_cnn_ce", 12, 8)
+    ref_model = copy.deepcopy(model)
+    model = model.to(DEV)
+    xd, td = x.to(DEV), t.to(DEV)
+    params, ref_params = list(model.parameters()), list(ref_model.parameters())
+    v = torch.randn(sum(p.numel() for p in params))
+    out, ref_out = model(xd), ref_model(x)
+    got = HessianFree._Gv(loss_fn(out, td), out, params, v.to(DEV))
+    want = O.Gv(loss_fn(ref_out, t), ref_out, ref_params, v)
+    assert max(errs(got, want)) < 1e-4
+    opt = HessianFree(model.parameters(), cg_max_iter=12)
+    orc = O.OracleHF(ref_model.parameters(), cg_max_iter=12)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(3):
+            f1 = opt.step(lambda: (lambda o: (loss_fn(o, td), o))(model(xd)))
+            f2 = orc.step(lambda: (lambda o: (loss_fn(o, t), o))(ref_model(x)))
+            assert f1 == pytest.approx(f2, rel=1e-3)
+    assert opt.state["num_cg_iters"] == orc.log["num_cg_iters"]
+
+
 def test_unlowered_conv_features_are_refused_loudly():
     model, loss_fn, x, t = make_case("small_cnn_ce", 4, 0)
     with pytest.raises(NotImplementedError, match="Hessian"):

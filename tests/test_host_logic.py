@@ -185,3 +185,18 @@ def test_conv_lowering_geometry():
     bad = nn.Sequential(nn.Conv2d(3, 8, 3), nn.ReLU())
     with pytest.raises(NotImplementedError, match="global average pool"):
         lower_module(bad, nn.MSELoss(), list(bad.parameters()), input_shape=(3, 12, 12))
+
+
+def test_graph_and_module_lowering_agree_on_a_conv_net():
+    model = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(), nn.Conv2d(8, 6, 3, stride=2, padding=1, bias=False), nn.ReLU(),
+                          nn.AvgPool2d(6), nn.Flatten(), nn.Linear(6, 4))
+    x, t = torch.rand(2, 3, 12, 12), torch.tensor([1, 2])
+    out = model(x)
+    g = lower_graph(nn.CrossEntropyLoss()(out, t), out, list(model.parameters()))
+    m = lower_module(model, nn.CrossEntropyLoss(), list(model.parameters()), input_shape=(3, 12, 12))
+    assert [l.signature() for l in g.layers] == [l.signature() for l in m.layers]
+    assert g.inputs is x or torch.equal(g.inputs, x)
+    pooled = nn.Sequential(nn.Conv2d(3, 8, 3), nn.Tanh(), nn.AdaptiveAvgPool2d(1), nn.Flatten())
+    o = pooled(x)
+    g2 = lower_graph(nn.MSELoss()(o, torch.rand(2, 8)), o, list(pooled.parameters()))
+    assert [(l.kind, l.act) for l in g2.layers] == [("conv2d", "tanh"), ("avgpool", "none")]
