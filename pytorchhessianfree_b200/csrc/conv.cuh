@@ -2,12 +2,14 @@
 //
 // A Conv2d layer is the linear layer  z = U W^T + b  on the UNFOLDED input U = im2col(a_{l-1}):
 //   rows of U   = output positions (n, oy, ox)            -> R_l = N * H_out * W_out
-//   columns of U = (c_in, ky, kx), c_in slowest           -> K_l = C_in * k_h * k_w
-// which is exactly how PyTorch flattens weight[C_out, C_in, k_h, k_w]: the layer's slice of the flat parameter
-// vector IS the [C_out, K_l] operand the tile engines read, the direction slice IS V_l, and the weight-gradient
-// contraction  cot^T U  lands in the flat layout without any reordering.  Activations are kept position-major
-// ("NHWC"): [R_l, C_out] with the library's 16-byte row pitch, i.e. the same [rows, width] matrices the fully connected
-// path uses, only with more rows than samples.  So the R-op, the transposed sweep and the weight gradients of a conv
+//   columns of U = (ky, kx, c_in), the tap slowest        -> K_l = k_h * k_w * C_in
+// Activations are kept position-major ("NHWC"): [R_l, C_out] with the library's 16-byte row pitch, i.e. the same
+// [rows, width] matrices the fully connected path uses, only with more rows than samples.  With the tap slowest, one
+// tap of one output position is a CONTIGUOUS run of C_in floats of the input row it reads: im2col and its transpose
+// move whole 16-byte groups, coalesced on both sides.  PyTorch flattens weight[C_out, C_in, k_h, k_w] with the channel
+// slowest, so the layer's weight and direction slices are re-ordered into [C_out, (tap, c_in)] operand copies (by the
+// split pass that makes the operand forms anyway: gemm_tc.cuh SplitSegment.perm_*), and the weight-gradient reduction
+// writes its result back in PyTorch's order: the flat-vector contract of the ABI is untouched.  So the R-op, the transposed sweep and the weight gradients of a conv
 // layer run on the tensor-core tile kernels unchanged; what this file adds is the data movement around them:
 //   im2col   a_{l-1} (or its tangent)  -> U       (once per linearisation for a, once per product for the tangent)
 //   fold     dU = cot W  -> cot_{l-1} = act'(a_{l-1}) * col2im(dU)   (gather form: deterministic, no atomics)
@@ -16,7 +18,7 @@
 // Every kernel can also write the split-precision image (gemm_simt.cuh: Image16) of what it produces, so that the
 // pair engine reads conv operands like any other.
 #pragma once
-#include "gemm_simt.cuh"
+#include "tc_common.cuh"
 
 namespace hf {
 
@@ -39,50 +41,62 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
-// U[(n, oy, ox), (c, ky, kx)] = src[(n, oy*s - p + ky, ox*s - p + kx), c]  (0 outside the map)
+// U[(n, oy, ox), (ky, kx, c)] = src[(n, oy*s - p + ky, ox*s - p + kx), c]  (0 outside the map); one thread per
+// (row, group of 4 columns of the pitched row)
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
                                                      int64_t n_samples, ConvGeom g, Image16 img, const int32_t* __restrict__ skip) {
   if (skip && *skip) return;
+  const int taps = g.kh * g.kw, K = taps * g.cin;
+  const int groups = ld_dst >> 2;  // 4-column groups of the PITCHED row: the padding columns get zeros
   const int64_t rows = n_samples * g.hout * g.wout;
-  const int64_t total = rows * g.cin;
-  const int K = g.cin * g.kh * g.kw;
+  const int64_t total = rows * groups;
+  const bool vec = g.cin % 4 == 0;  // a group never straddles two taps, and the source run is 16-byte aligned
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % g.cin);
-    const int64_t r = i / g.cin;
+    const int k0 = (int)(i % groups) * 4;
+    const int64_t r = i / groups;
     const int ox = (int)(r % g.wout), oy = (int)((r / g.wout) % g.hout);
     const int64_t s = r / ((int64_t)g.wout * g.hout);
-    float* d = dst + r * ld_dst + c * g.kh * g.kw;
-    for (int ky = 0; ky < g.kh; ++ky) {
-      const int iy = oy * g.stride - g.pad + ky;
-      for (int kx = 0; kx < g.kw; ++kx) {
-        const int ix = ox * g.stride - g.pad + kx;
-        float v = 0.f;
-        if (iy >= 0 && iy < g.hin && ix >= 0 && ix < g.win) v = src[((s * g.hin + iy) * g.win + ix) * ld_src + c];
-        d[ky * g.kw + kx] = v;
-        if (img.hi) store_image1(img, r, c * g.kh * g.kw + ky * g.kw + kx, v);
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+      if (k0 < K) {
+        const int tap = k0 / g.cin, c = k0 % g.cin;
+        const int iy = oy * g.stride - g.pad + tap / g.kw, ix = ox * g.stride - g.pad + tap % g.kw;
+        if (iy >= 0 && iy < g.hin && ix >= 0 && ix < g.win) {
+          const float4 v = *reinterpret_cast<const float4*>(src + ((s * g.hin + iy) * g.win + ix) * ld_src + c);
+          x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + e;
+        if (k >= K) continue;
+        const int tap = k / g.cin, c = k % g.cin;
+        const int iy = oy * g.stride - g.pad + tap / g.kw, ix = ox * g.stride - g.pad + tap % g.kw;
+        if (iy >= 0 && iy < g.hin && ix >= 0 && ix < g.win) x[e] = src[((s * g.hin + iy) * g.win + ix) * ld_src + c];
       }
     }
-    if (c == g.cin - 1)
-      for (int k = K; k < ld_dst; ++k) dst[r * ld_dst + k] = 0.f;  // the 16-byte row pitch's padding
+    *reinterpret_cast<float4*>(dst + r * ld_dst + k0) = make_float4(x[0], x[1], x[2], x[3]);
+    if (img.hi) st4_image(img, r, k0, 4, x);  // image pitch pad8(K) >= pad4(K): in range
   }
 }
 
-__device__ __forceinline__ float conv_act_d1(int act, float s) { return act_d1(act, s); }
-
 // cot_prev[(n, y, x), c] = act'(a_prev) * sum over the taps (ky, kx) that read input position (y, x):
-//   dU[(n, oy, ox), (c, ky, kx)]  with  oy*s - p + ky = y,  ox*s - p + kx = x
+//   dU[(n, oy, ox), (ky, kx, c)]  with  oy*s - p + ky = y,  ox*s - p + kx = x;   one thread per (input row, 4 channels)
 __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ dU, int ld_du, const float* __restrict__ a_prev, int ld_a, int act_prev,
                                                    float* __restrict__ dst, int64_t n_samples, ConvGeom g, Image16 img,
                                                    const int32_t* __restrict__ skip) {
   if (skip && *skip) return;
+  const int groups = (g.cin + 3) >> 2;
   const int64_t rows_in = n_samples * g.hin * g.win;
-  const int64_t total = rows_in * g.cin;
+  const int64_t total = rows_in * groups;
+  const bool vec = g.cin % 4 == 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % g.cin);
-    const int64_t r = i / g.cin;
+    const int c0 = (int)(i % groups) * 4, cnt = min(4, g.cin - c0);
+    const int64_t r = i / groups;
     const int x = (int)(r % g.win), y = (int)((r / g.win) % g.hin);
     const int64_t s = r / ((int64_t)g.win * g.hin);
-    float acc = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int ky = 0; ky < g.kh; ++ky) {
       const int ty = y + g.pad - ky;
       if (ty < 0 || ty % g.stride) continue;
@@ -93,12 +107,23 @@ __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ dU,
         if (tx < 0 || tx % g.stride) continue;
         const int ox = tx / g.stride;
         if (ox >= g.wout) continue;
-        acc += dU[((s * g.hout + oy) * g.wout + ox) * ld_du + (c * g.kh + ky) * g.kw + kx];
+        const float* p = dU + ((s * g.hout + oy) * g.wout + ox) * ld_du + (ky * g.kw + kx) * g.cin + c0;
+        if (vec) {
+          const float4 v = *reinterpret_cast<const float4*>(p);
+          acc[0] += v.x, acc[1] += v.y, acc[2] += v.z, acc[3] += v.w;
+        } else {
+          for (int e = 0; e < cnt; ++e) acc[e] += p[e];
+        }
       }
     }
-    const float v = act_prev == HF_ACT_NONE ? acc : acc * act_d1(act_prev, a_prev[r * ld_a + c]);
-    dst[r * ld_a + c] = v;
-    if (img.hi) store_image1(img, r, c, v);
+    if (act_prev != HF_ACT_NONE)
+      for (int e = 0; e < cnt; ++e) acc[e] *= act_d1(act_prev, a_prev[r * ld_a + c0 + e]);
+    if (vec) {
+      *reinterpret_cast<float4*>(dst + r * ld_a + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+      for (int e = 0; e < cnt; ++e) dst[r * ld_a + c0 + e] = acc[e];
+    }
+    if (img.hi) st4_image(img, r, c0, cnt, acc);
   }
 }
 

@@ -295,14 +295,17 @@ static __global__ void reduce_partials_kernel(const float* __restrict__ part, in
 }
 
 // Two reductions in one launch: a weight-gradient slice and the bias slice that follows it in the flat layout.
+// perm_taps > 0 (convolution layers, conv.cuh): the partial tiles hold the weight slice with columns (tap, c_in); it is
+// written back with columns (c_in, tap), the order of PyTorch's flat parameter vector.
 static __global__ void reduce_partials2_kernel(const float* __restrict__ partW, int splitsW, int64_t countW,
                                                float* __restrict__ outW, const float* __restrict__ partB, int splitsB,
                                                int64_t countB, float* __restrict__ outB, float scale, int accumulate,
-                                               const int32_t* __restrict__ skip) {
+                                               const int32_t* __restrict__ skip, int perm_cin = 0, int perm_taps = 0) {
   if (skip && *skip) return;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
   // weight slice, 4 elements per thread: all split loads of a group are independent, so they are in flight together
-  const bool vec = countW % 4 == 0 && ((reinterpret_cast<uintptr_t>(partW) | reinterpret_cast<uintptr_t>(outW)) & 15u) == 0;
+  const bool vec = perm_taps == 0 && countW % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(partW) | reinterpret_cast<uintptr_t>(outW)) & 15u) == 0;
   const int64_t nvec = vec ? countW / 4 : 0;
   for (int64_t v = tid; v < nvec; v += nthreads) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -328,7 +331,12 @@ static __global__ void reduce_partials2_kernel(const float* __restrict__ partW, 
 #pragma unroll 8
     for (int z = 0; z < splits; ++z) s += part[(int64_t)z * stride + j];
     float* out = w ? outW : outB;
-    out[j] = (accumulate ? out[j] : 0.f) + scale * s;
+    int64_t dst = j;
+    if (w && perm_taps > 0) {
+      const int64_t K = (int64_t)perm_cin * perm_taps, o = j / K, col = j % K;  // col = tap * c_in + c
+      dst = o * K + (col % perm_cin) * perm_taps + col / perm_cin;
+    }
+    out[dst] = (accumulate ? out[dst] : 0.f) + scale * s;
   }
 }
 

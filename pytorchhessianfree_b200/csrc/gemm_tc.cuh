@@ -32,6 +32,9 @@ struct SplitSegment {
   int64_t ld32;
   Image16 img;   // optional
   int square;    // 1: every element is squared first (operands of the empirical-Fisher contraction)
+  // perm_taps > 0: the columns are re-ordered on the way, dst column tap*perm_cin + c = src column c*perm_taps + tap:
+  // a convolution weight [C_out, C_in, k_h, k_w] as PyTorch flattens it -> the tap-major operand conv.cuh contracts with
+  int perm_cin, perm_taps;
 };
 constexpr int kMaxSplitSegments = 20;
 struct SplitTable {

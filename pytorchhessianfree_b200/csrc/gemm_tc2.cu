@@ -265,7 +265,12 @@ __global__ void __launch_bounds__(256) split_segments_kernel(SplitTable t) {
     const int c = (int)(i % groups) * 4, cnt = min(4, s.cols - c);
     float x[4] = {0.f, 0.f, 0.f, 0.f};
     const float* src = s.src + r * s.ld_src + c;
-    if (vec && cnt == 4) {
+    if (s.perm_taps > 0) {
+      for (int e = 0; e < cnt; ++e) {
+        const int j = c + e;  // destination column (tap, channel) <- source column (channel, tap)
+        x[e] = s.src[r * s.ld_src + (j % s.perm_cin) * s.perm_taps + j / s.perm_cin];
+      }
+    } else if (vec && cnt == 4) {
       const float4 v = *reinterpret_cast<const float4*>(src);
       x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
     } else {

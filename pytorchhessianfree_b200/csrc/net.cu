@@ -448,7 +448,7 @@ static int run_gemm(const hf_net* net, const GemmArgs& g, cudaStream_t stream, b
 // out_b[out] (+)= scale * column sums of d.  The column sums either come for free from the tensor-core kernel that
 // produced d (`col_tiles` partial rows already in lin->colbuf) or from one colsum launch; ONE launch then reduces
 // both partial sets in fixed order (deterministic) into the flat vector.
-static int layer_gradient(hf_lin* lin, int64_t rows, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
+static int layer_gradient(hf_lin* lin, const Layer& L, int64_t rows, int M, int N, int n_pairs, const Operand* A, const Operand* B, int square,
                           float* out_w, const float* d, int ld_d, int col_tiles, float* colbuf, float* out_b, float scale,
                           int accumulate, const int32_t* skip, cudaStream_t stream, bool main_scratch = false) {
   int splits_w = 0, splits_b = 0;
@@ -511,8 +511,9 @@ static int layer_gradient(hf_lin* lin, int64_t rows, int M, int N, int n_pairs, 
   if (count_w + count_b == 0) return HF_OK;
   int64_t blocks = (count_w / 4 + count_b + 255) / 256 + 1;
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  const int taps = L.unfold ? L.geom.kh * L.geom.kw : 0;  // unfolded operands are tap-major: write back channel-major
   reduce_partials2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, splits_w, count_w, out_w, colbuf, splits_b,
-                                                               count_b, out_b, scale, accumulate, skip);
+                                                               count_b, out_b, scale, accumulate, skip, L.geom.cin, taps);
   HF_LAUNCH_CHECK();
   return HF_OK;
 }
@@ -537,7 +538,8 @@ static int prepare_direction(hf_lin* lin, const float* v, int l_begin, int l_end
     if (!lin->vpad[l] && !img) continue;
     if (img) vi.base = lin->vpad[l] ? lin->vpad[l] : v + L.w_off;
     t.seg[t.count++] = SplitSegment{v + L.w_off, L.out, L.in, L.in, lin->vpad[l], pad4(L.in),
-                                    img ? Image16{vi.hi, vi.plane, pad8(L.in)} : Image16{nullptr, 0, 0}};
+                                    img ? Image16{vi.hi, vi.plane, pad8(L.in)} : Image16{nullptr, 0, 0}, 0,
+                                    L.geom.cin, L.unfold ? L.geom.kh * L.geom.kw : 0};
     if (t.count == kMaxSplitSegments) {
       int rc = launch_split(t, stream);
       if (rc) return rc;
@@ -585,8 +587,8 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
     if (cur) {
       const float* cur_mat = cur;
       if (L.unfold) {  // the tangent of the unfolded input is the unfolded tangent
-        im2col_kernel<<<conv_blocks(rows_out(lin, l) * L.geom.cin), 256, 0, stream>>>(cur, pad4(L.geom.cin), lin->ru, pad4(L.in), lin->N, L.geom,
-                                                                                     image_for(lin, lin->ru, L.in), skip);
+        im2col_kernel<<<conv_blocks(rows_out(lin, l) * (pad4(L.in) / 4)), 256, 0, stream>>>(cur, pad4(L.geom.cin), lin->ru, pad4(L.in), lin->N,
+                                                                                           L.geom, image_for(lin, lin->ru, L.in), skip);
         HF_LAUNCH_CHECK();
         cur_mat = lin->ru;
       }
@@ -784,7 +786,7 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       // it runs there (own split-K scratch) while the side stream finishes the upper layers' reductions.
       const bool on_main = fork && l == net->first_trainable && lin->partial_main != nullptr;
       if (fork && !on_main) HF_CUDA(cudaStreamWaitEvent(gstream, lin->ev[l], 0));
-      int rc = layer_gradient(lin, rows, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
+      int rc = layer_gradient(lin, L, rows, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
                               cur_col_tiles, lin->colbuf[l], has_b ? out + L.b_off : nullptr, scale, accumulate, skip,
                               on_main ? stream : gstream, on_main);
       if (rc) return rc;
@@ -806,7 +808,7 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
         int rc = run_gemm(net, g, stream);
         if (rc) return rc;
         float* dst = lin->cot[l - 1];
-        fold_kernel<<<conv_blocks(rows_in(lin, l) * L.geom.cin), 256, 0, stream>>>(lin->du, pad4(L.in), lin->a[l - 1], pad4(L.geom.cin), Lp.act, dst,
+        fold_kernel<<<conv_blocks(rows_in(lin, l) * ((L.geom.cin + 3) / 4)), 256, 0, stream>>>(lin->du, pad4(L.in), lin->a[l - 1], pad4(L.geom.cin), Lp.act, dst,
                                                                                   lin->N, L.geom, image_for(lin, dst, L.geom.cin), skip);
         HF_LAUNCH_CHECK();
         if (fork) HF_CUDA(cudaEventRecord(lin->ev[l - 1], stream));
@@ -1034,18 +1036,23 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   float* pfwd = fwd_max ? (float*)take(sizeof(float) * fwd_max * N * pad4(net->classes)) : nullptr;
   if (lin) lin->partial_fwd = pfwd, lin->fwd_splits_max = fwd_max, lin->fwd_splits = 0, lin->fwd_bias = nullptr;
   if (lin) lin->wpad.assign(nl, nullptr), lin->vpad.assign(nl, nullptr);
-  if (!loss_only && net->engine == 1)
-    for (int l = net->first_trainable; l < nl; ++l) {
-      const Layer& L = net->L[l];
-      // in place needs a 16-byte row pitch AND a 16-byte aligned slice start (the flat offset of a layer depends on
-      // the sizes of all layers before it: after a 30- or 250-wide layer every later slice is misaligned)
-      if (L.kind == HF_LAYER_AVGPOOL) continue;
+  for (int l = 0; l < nl; ++l) {
+    const Layer& L = net->L[l];
+    if (L.kind == HF_LAYER_AVGPOOL) continue;
+    // Unfolded convolutions always contract with a re-ordered (tap-major) copy of their weight, in every engine and
+    // also on the loss-only path.  Otherwise a copy is only needed by the tensor engines, when TMA cannot address the
+    // flat slice in place: that needs a 16-byte row pitch AND a 16-byte aligned slice start (the flat offset of a
+    // layer depends on the sizes of all layers before it: after a 30- or 250-wide layer every later slice is misaligned)
+    bool need = L.unfold;
+    if (!need && !loss_only && net->engine == 1 && l >= net->first_trainable) {
       const bool aligned = L.w_off >= 0 ? L.w_off % 4 == 0 : (reinterpret_cast<uintptr_t>(L.w_frozen) & 15u) == 0;
-      if (L.in % 4 == 0 && aligned) continue;
-      float* wp = (float*)take(sizeof(float) * L.out * pad4(L.in));
-      float* vp = L.w_off >= 0 ? (float*)take(sizeof(float) * L.out * pad4(L.in)) : nullptr;
-      if (lin) lin->wpad[l] = wp, lin->vpad[l] = vp;
+      need = !(L.in % 4 == 0 && aligned);
     }
+    if (!need) continue;
+    float* wp = (float*)take(sizeof(float) * L.out * pad4(L.in));
+    float* vp = (!loss_only && L.w_off >= 0 && l >= net->first_trainable) ? (float*)take(sizeof(float) * L.out * pad4(L.in)) : nullptr;
+    if (lin) lin->wpad[l] = wp, lin->vpad[l] = vp;
+  }
   // fused output head for GGN products: narrow trainable last layer without activation on top of a trainable stack
   bool head_ok = false;
   HeadPlan hp = {};
@@ -1210,6 +1217,28 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
         d_x, lin->xn, lin->N, L0.geom.cin, L0.s_in, pad4(L0.geom.cin), image_for(lin, lin->xn, L0.geom.cin));
     HF_LAUNCH_CHECK();
   }
+  const Image16 none = {nullptr, 0, 0};
+  {
+    // Operand forms of the weights (constant for the life of this linearisation), in one launch: the tap-major copies
+    // unfolded convolutions contract with, the 16-byte-pitched FP32 copies of slices TMA cannot address in place, and
+    // (pair engine) the split-precision images.
+    SplitTable t;
+    t.count = 0, t.skip = nullptr;
+    int rc = HF_OK;
+    for (int l = 0; l < nl && !rc; ++l) {
+      const Layer& L = net->L[l];
+      if (L.kind == HF_LAYER_AVGPOOL) continue;
+      const bool img = lin->use_images && lin->w_img[l].hi;
+      if (!lin->wpad[l] && !img) continue;
+      if (img) lin->w_img[l].base = lin->wpad[l] ? lin->wpad[l] : weight_ptr(L, d_theta);
+      t.seg[t.count++] = SplitSegment{weight_ptr(L, d_theta), L.out, L.in, L.in, lin->wpad[l], pad4(L.in),
+                                      img ? Image16{lin->w_img[l].hi, lin->w_img[l].plane, pad8(L.in)} : none, 0,
+                                      L.geom.cin, L.unfold ? L.geom.kh * L.geom.kw : 0};
+      if (t.count == kMaxSplitSegments) rc = launch_split(t, stream), t.count = 0;
+    }
+    if (!rc) rc = launch_split(t, stream);
+    if (rc) return rc;
+  }
   for (int l = 0; l < nl; ++l) {
     const Layer& L = net->L[l];
     if (L.kind == HF_LAYER_AVGPOOL) {
@@ -1220,8 +1249,8 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     }
     if (L.unfold) {  // the unfolded input (+ its image) stays resident: every product of the solve contracts with it
       const float* src = l == 0 ? lin->xn : lin->a[l - 1];
-      im2col_kernel<<<conv_blocks(rows_out(lin, l) * L.geom.cin), 256, 0, stream>>>(src, pad4(L.geom.cin), lin->U[l], pad4(L.in), lin->N, L.geom,
-                                                                                   image_for(lin, lin->U[l], L.in), nullptr);
+      im2col_kernel<<<conv_blocks(rows_out(lin, l) * (pad4(L.in) / 4)), 256, 0, stream>>>(src, pad4(L.geom.cin), lin->U[l], pad4(L.in), lin->N,
+                                                                                         L.geom, image_for(lin, lin->U[l], L.in), nullptr);
       HF_LAUNCH_CHECK();
     }
     int ld_in = 0;
@@ -1229,7 +1258,7 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     GemmArgs g = blank_gemm();
     g.M = (int)rows_out(lin, l), g.N = L.out, g.K = L.in, g.n_pairs = 1;
     g.A[0] = op_kc(a_in, ld_in);
-    g.B[0] = op_kc(weight_ptr(L, d_theta), L.in);
+    g.B[0] = L.unfold ? op_kc(lin->wpad[l], pad4(L.in)) : op_kc(weight_ptr(L, d_theta), L.in);  // (tap-major copy for unfolded inputs)
     g.C = lin->a[l], g.ldc = pad4(L.out);
     g.epi = EPI_BIAS_ACT, g.act = L.act, g.bias = bias_ptr(L, d_theta);
     // The linearisation point fixes the ReLU masks for the whole solve, so it is evaluated in plain FP32: the
@@ -1243,9 +1272,8 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
     if (rc) return rc;
   }
   {
-    // Operand forms of everything that stays constant for the life of this linearisation, in one launch: the
-    // 16-byte-pitched FP32 copies of weights whose flat slice TMA cannot address in place, and (pair engine) the
-    // split-precision images of the inputs, the activations and the weights.
+    // (pair engine) the split-precision images of the inputs and the activations, constant for the life of this
+    // linearisation, in one launch
     SplitTable t;
     t.count = 0, t.skip = nullptr;
     auto push = [&](const SplitSegment& sg) -> int {
@@ -1255,7 +1283,6 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
       t.count = 0;
       return rc;
     };
-    const Image16 none = {nullptr, 0, 0};
     int rc = HF_OK;
     if (lin->use_images) {
       if (net->L[0].kind == HF_LAYER_LINEAR) {
@@ -1265,15 +1292,6 @@ int hf_lin_forward(hf_lin_t* lin, const float* d_theta, const float* d_x, const 
       for (int l = 0; l < nl - 1 && !rc; ++l)
         rc = push(SplitSegment{lin->a[l], rows_out(lin, l), net->L[l].out, pad4(net->L[l].out), nullptr, 0,
                                image_for(lin, lin->a[l], net->L[l].out)});
-    }
-    for (int l = net->first_trainable; l < nl && !rc && !(lin->flags & HF_LIN_LOSS_ONLY); ++l) {
-      const Layer& L = net->L[l];
-      if (L.kind == HF_LAYER_AVGPOOL) continue;
-      const bool img = lin->use_images && lin->w_img[l].hi;
-      if (!lin->wpad[l] && !img) continue;
-      if (img) lin->w_img[l].base = lin->wpad[l] ? lin->wpad[l] : weight_ptr(L, d_theta);
-      rc = push(SplitSegment{weight_ptr(L, d_theta), L.out, L.in, L.in, lin->wpad[l], pad4(L.in),
-                             img ? Image16{lin->w_img[l].hi, lin->w_img[l].plane, pad8(L.in)} : none});
     }
     if (!rc) rc = launch_split(t, stream);
     if (rc) return rc;
