@@ -160,8 +160,8 @@ typedef struct hf_lin hf_lin_t;
  * c_in*k_h*k_w, the weight [out, c_in, k_h, k_w] sits at w_offset exactly as PyTorch flattens it, inputs are NCHW when it
  * is the first layer.  HF_LAYER_AVGPOOL: average over the whole [h_in, w_in] map (in_features = out_features = c_in, no
  * parameters); the layers after it see one row per sample again.  The last layer must produce one row per sample.
- * Conv nets support loss, gradient and GGN products (examples/run_allcnnc_cifar100_deepobs.py, eval mode); Hessian
- * products and the Fisher diagonal of conv nets are not lowered yet (HF_ERR_UNSUPPORTED). */
+ * Conv nets support loss, gradient, GGN and Hessian products (examples/run_allcnnc_cifar100_deepobs.py, eval mode); the
+ * Fisher diagonal of conv nets is not lowered yet (HF_ERR_UNSUPPORTED). */
 enum hf_layer_kind { HF_LAYER_LINEAR = 0, HF_LAYER_CONV2D = 1, HF_LAYER_AVGPOOL = 2 };
 
 typedef struct {

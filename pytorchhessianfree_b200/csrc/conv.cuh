@@ -9,8 +9,9 @@
 // move whole 16-byte groups, coalesced on both sides.  PyTorch flattens weight[C_out, C_in, k_h, k_w] with the channel
 // slowest, so the layer's weight and direction slices are re-ordered into [C_out, (tap, c_in)] operand copies (by the
 // split pass that makes the operand forms anyway: gemm_tc.cuh SplitSegment.perm_*), and the weight-gradient reduction
-// writes its result back in PyTorch's order: the flat-vector contract of the ABI is untouched.  So the R-op, the transposed sweep and the weight gradients of a conv
-// layer run on the tensor-core tile kernels unchanged; what this file adds is the data movement around them:
+// writes its result back in PyTorch's order: the flat-vector contract of the ABI is untouched.  So the R-op, the
+// transposed sweep and the weight gradients of a conv layer run on the tensor-core tile kernels unchanged; what this
+// file adds is the data movement around them:
 //   im2col   a_{l-1} (or its tangent)  -> U       (once per linearisation for a, once per product for the tangent)
 //   fold     dU = cot W  -> cot_{l-1} = act'(a_{l-1}) * col2im(dU)   (gather form: deterministic, no atomics)
 //   pool / unpool  for a global average pool (All-CNN-C: 6x6 -> 1x1 in front of the loss)
@@ -83,9 +84,13 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ s
 
 // cot_prev[(n, y, x), c] = act'(a_prev) * sum over the taps (ky, kx) that read input position (y, x):
 //   dU[(n, oy, ox), (ky, kx, c)]  with  oy*s - p + ky = y,  ox*s - p + kx = x;   one thread per (input row, 4 channels)
+// Optional, for Hessian products (Pearlmutter): ga_out receives the folded value BEFORE the activation derivative
+// (dloss/da of the layer below, kept by the gradient pass); h_ga / h_rz add the second-order activation term
+// ga * act''(a) * R{z} of the layer below (the conv analogue of EPI_DACT_H).
 __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ dU, int ld_du, const float* __restrict__ a_prev, int ld_a, int act_prev,
                                                    float* __restrict__ dst, int64_t n_samples, ConvGeom g, Image16 img,
-                                                   const int32_t* __restrict__ skip) {
+                                                   const int32_t* __restrict__ skip, float* __restrict__ ga_out = nullptr,
+                                                   const float* __restrict__ h_ga = nullptr, const float* __restrict__ h_rz = nullptr) {
   if (skip && *skip) return;
   const int groups = (g.cin + 3) >> 2;
   const int64_t rows_in = n_samples * g.hin * g.win;
@@ -116,8 +121,14 @@ __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ dU,
         }
       }
     }
+    if (ga_out)
+      for (int e = 0; e < cnt; ++e) ga_out[r * ld_a + c0 + e] = acc[e];
     if (act_prev != HF_ACT_NONE)
-      for (int e = 0; e < cnt; ++e) acc[e] *= act_d1(act_prev, a_prev[r * ld_a + c0 + e]);
+      for (int e = 0; e < cnt; ++e) {
+        const float sa = a_prev[r * ld_a + c0 + e];
+        acc[e] *= act_d1(act_prev, sa);
+        if (h_ga) acc[e] += h_ga[r * ld_a + c0 + e] * act_d2(act_prev, sa) * h_rz[r * ld_a + c0 + e];
+      }
     if (vec) {
       *reinterpret_cast<float4*>(dst + r * ld_a + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     } else {
@@ -147,7 +158,8 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const float* __restrict__ 
 // dst[(n, p), c] = cur[n, c] / hw * act'(a_prev[(n, p), c])   (transposed average pool, through the previous activation)
 __global__ void __launch_bounds__(256) unpool_kernel(const float* __restrict__ cur, int ld, const float* __restrict__ a_prev, int act_prev,
                                                      float* __restrict__ dst, int64_t n_samples, int hw, int c, Image16 img,
-                                                     const int32_t* __restrict__ skip) {
+                                                     const int32_t* __restrict__ skip, float* __restrict__ ga_out = nullptr,
+                                                     const float* __restrict__ h_ga = nullptr, const float* __restrict__ h_rz = nullptr) {
   if (skip && *skip) return;
   const int64_t total = n_samples * hw * (int64_t)c;
   const float inv = 1.f / (float)hw;
@@ -156,7 +168,12 @@ __global__ void __launch_bounds__(256) unpool_kernel(const float* __restrict__ c
     const int64_t r = i / c;
     const int64_t s = r / hw;
     float v = cur[s * ld + ch] * inv;
-    if (act_prev != HF_ACT_NONE) v *= act_d1(act_prev, a_prev[r * ld + ch]);
+    if (ga_out) ga_out[r * ld + ch] = v;
+    if (act_prev != HF_ACT_NONE) {
+      const float sa = a_prev[r * ld + ch];
+      v *= act_d1(act_prev, sa);
+      if (h_ga) v += h_ga[r * ld + ch] * act_d2(act_prev, sa) * h_rz[r * ld + ch];
+    }
     dst[r * ld + ch] = v;
     if (img.hi) store_image1(img, r, ch, v);
   }

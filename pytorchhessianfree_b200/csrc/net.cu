@@ -104,6 +104,7 @@ struct hf_lin {
   // the largest unfolded size: the unfolded tangent of the R-op and dU = cot W of the transposed sweep
   float* xn;
   std::vector<float*> U;
+  std::vector<float*> RU;  // HESSIAN: the unfolded R{a_{l-1}} of every unfolded layer, kept for the transposed sweep
   float* ru;
   float* du;
   const float* pending_cur;   // phased sweep: cotangent of the first trainable layer, left by phase 0 for phase 1
@@ -566,12 +567,13 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
     if (L.kind == HF_LAYER_AVGPOOL) {
       // the tangent of a global average pool is the pool of the tangent
       if (cur) {
-        float* dst = lin->buf[which];
+        const bool keep_ra = hessian && l < nl - 1;
+        float* dst = keep_ra ? lin->ra[l] : lin->buf[which];
         avgpool_kernel<<<conv_blocks(lin->N * (int64_t)L.out), 256, 0, stream>>>(cur, ld_out, dst, lin->N, L.s_in, L.out,
                                                                                   image_for(lin, dst, L.out), skip);
         HF_LAUNCH_CHECK();
         cur = dst;
-        which ^= 1;
+        if (!keep_ra) which ^= 1;
       }
       continue;
     }
@@ -586,11 +588,12 @@ static int rop_forward(hf_lin* lin, const float* theta, const float* v, bool hes
     }
     if (cur) {
       const float* cur_mat = cur;
-      if (L.unfold) {  // the tangent of the unfolded input is the unfolded tangent
-        im2col_kernel<<<conv_blocks(rows_out(lin, l) * (pad4(L.in) / 4)), 256, 0, stream>>>(cur, pad4(L.geom.cin), lin->ru, pad4(L.in), lin->N,
-                                                                                           L.geom, image_for(lin, lin->ru, L.in), skip);
+      if (L.unfold) {  // the tangent of the unfolded input is the unfolded tangent (kept per layer for Hessian products)
+        float* ru = (hessian && lin->RU[l]) ? lin->RU[l] : lin->ru;
+        im2col_kernel<<<conv_blocks(rows_out(lin, l) * (pad4(L.in) / 4)), 256, 0, stream>>>(cur, pad4(L.geom.cin), ru, pad4(L.in), lin->N,
+                                                                                           L.geom, image_for(lin, ru, L.in), skip);
         HF_LAUNCH_CHECK();
-        cur_mat = lin->ru;
+        cur_mat = ru;
       }
       g.A[np] = with_image(lin, op_kc(cur_mat, pad4(L.in)), L.in), g.B[np] = w_operand(lin, l, theta, true);
       ++np;
@@ -763,9 +766,11 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       // derivative of the layer below (which the kernel producing cot[l-1] always applies)
       if (l - 1 < net->first_trainable) break;  // nothing trainable below
       const Layer& Lp = net->L[l - 1];
-      float* dst = lin->cot[l - 1];
-      unpool_kernel<<<conv_blocks(rows_out(lin, l - 1) * (int64_t)L.out), 256, 0, stream>>>(cur, ld_out, lin->a[l - 1], Lp.act, dst, lin->N, L.s_in,
-                                                                                            L.out, image_for(lin, dst, L.out), skip);
+      float* dst = keep ? lin->delta[l - 1] : lin->cot[l - 1];
+      const bool second = mode == BACK_HESSIAN && curved(Lp.act);
+      unpool_kernel<<<conv_blocks(rows_out(lin, l - 1) * (int64_t)L.out), 256, 0, stream>>>(
+          cur, ld_out, lin->a[l - 1], Lp.act, dst, lin->N, L.s_in, L.out, image_for(lin, dst, L.out), skip,
+          (keep && curved(Lp.act)) ? lin->ga[l - 1] : nullptr, second ? lin->ga[l - 1] : nullptr, second ? lin->rz[l - 1] : nullptr);
       HF_LAUNCH_CHECK();
       if (fork) HF_CUDA(cudaEventRecord(lin->ev[l - 1], stream));
       cur = dst, cur_col_tiles = 0;
@@ -779,7 +784,8 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       int np = 0;
       A[np] = with_image(lin, op_mnc(cur, ld_out), L.out), B[np] = with_image(lin, op_mnc(a_in, ld_in), L.in), ++np;
       if (mode == BACK_HESSIAN && l > net->first_trainable) {
-        A[np] = op_mnc(lin->delta[l], ld_out), B[np] = op_mnc(lin->ra[l - 1], ld_in), ++np;
+        // delta_l^T R{input of the layer}: the kept unfolded tangent for an unfolded convolution
+        A[np] = op_mnc(lin->delta[l], ld_out), B[np] = op_mnc(L.unfold ? lin->RU[l] : lin->ra[l - 1], ld_in), ++np;
       }
       const bool has_b = L.has_bias && L.b_off >= 0;
       // The first trainable layer's gradient is the end of the chain: the caller's stream has nothing left to do, so
@@ -801,15 +807,20 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       if (L.unfold) {
         // convolution: dU = cot W is the cotangent of the UNFOLDED input; fold it back onto the input map (gather
         // form) and apply the activation derivative of the layer below there
+        if (mode == BACK_HESSIAN && L.w_off >= 0) {
+          g.A[np] = op_kc(lin->delta[l], ld_out), g.B[np] = v_operand(lin, l, v, false), ++np;
+        }
         g.n_pairs = np;
         g.C = lin->du, g.ldc = pad4(L.in);
         g.epi = EPI_STORE;
         g.skip = skip;
         int rc = run_gemm(net, g, stream);
         if (rc) return rc;
-        float* dst = lin->cot[l - 1];
-        fold_kernel<<<conv_blocks(rows_in(lin, l) * ((L.geom.cin + 3) / 4)), 256, 0, stream>>>(lin->du, pad4(L.in), lin->a[l - 1], pad4(L.geom.cin), Lp.act, dst,
-                                                                                  lin->N, L.geom, image_for(lin, dst, L.geom.cin), skip);
+        float* dst = keep ? lin->delta[l - 1] : lin->cot[l - 1];
+        const bool second = mode == BACK_HESSIAN && curved(Lp.act);
+        fold_kernel<<<conv_blocks(rows_in(lin, l) * ((L.geom.cin + 3) / 4)), 256, 0, stream>>>(
+            lin->du, pad4(L.in), lin->a[l - 1], pad4(L.geom.cin), Lp.act, dst, lin->N, L.geom, image_for(lin, dst, L.geom.cin), skip,
+            (keep && curved(Lp.act)) ? lin->ga[l - 1] : nullptr, second ? lin->ga[l - 1] : nullptr, second ? lin->rz[l - 1] : nullptr);
         HF_LAUNCH_CHECK();
         if (fork) HF_CUDA(cudaEventRecord(lin->ev[l - 1], stream));
         cur = dst, cur_col_tiles = 0;
@@ -995,7 +1006,7 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   float* xn = net->L[0].kind != HF_LAYER_LINEAR ? (float*)take(sizeof(float) * N * net->L[0].s_in * pad4(net->L[0].geom.cin)) : nullptr;
   float* ru = max_unfold ? (float*)take(sizeof(float) * N * max_unfold) : nullptr;
   float* du = (max_unfold && !loss_only) ? (float*)take(sizeof(float) * N * max_unfold) : nullptr;
-  if (lin) lin->xn = xn, lin->ru = ru, lin->du = du, lin->U.assign(nl, nullptr);
+  if (lin) lin->xn = xn, lin->ru = ru, lin->du = du, lin->U.assign(nl, nullptr), lin->RU.assign(nl, nullptr);
   if (loss_only) {
     // activations are not kept: alternate between two buffers; unfolded inputs share one scratch matrix
     float* b0 = (float*)take(sizeof(float) * N * net->max_act);
@@ -1140,7 +1151,11 @@ static size_t carve(const hf_net* net, int64_t N, int flags, char* base, hf_lin*
   double* lp = (double*)take(sizeof(double) * lb);
   if (hess && !loss_only) {
     for (int l = net->first_trainable; l < nl; ++l) {
-      const size_t bytes = sizeof(float) * N * pad4(net->L[l].out);
+      const size_t bytes = sizeof(float) * N * net->L[l].s_out * pad4(net->L[l].out);
+      if (net->L[l].unfold && l > net->first_trainable) {
+        float* ruk = (float*)take(sizeof(float) * N * net->L[l].s_out * pad4(net->L[l].in));
+        if (lin) lin->RU[l] = ruk;
+      }
       float* d = (l < nl - 1) ? (float*)take(bytes) : nullptr;  // the last layer's delta is deltaL
       float* r = (l < nl - 1) ? (float*)take(bytes) : nullptr;
       float* g = nullptr;
@@ -1169,8 +1184,6 @@ int hf_lin_create(const hf_net_t* net, int64_t batch, int32_t flags, void* d_wor
   HF_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255u) == 0, HF_ERR_WORKSPACE, "hf_lin_create: workspace must be 256-byte aligned");
   if ((flags & HF_LIN_HESSIAN) && net->L.back().act != HF_ACT_NONE)
     HF_REQUIRE(false, HF_ERR_UNSUPPORTED, "Hessian products with an activation after the last layer are not supported");
-  HF_REQUIRE(!((flags & HF_LIN_HESSIAN) && net->has_conv), HF_ERR_UNSUPPORTED,
-             "Hessian products of convolutional nets are not lowered yet (GGN products, gradient and loss are)");
   const size_t need = carve(net, batch, flags, nullptr, nullptr);
   HF_REQUIRE(workspace_bytes >= need, HF_ERR_WORKSPACE, "hf_lin_create: workspace has %zu bytes, need %zu", workspace_bytes, need);
   hf_lin* lin = new (std::nothrow) hf_lin();
