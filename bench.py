@@ -365,6 +365,9 @@ def run_native(args):
         roof, extra = kernel_rooflines(lib, local_prob, theta, dev, pk, engine)
         if world == 1:
             extra["cfg2"] = cfg2_block(lib, dev, pk, engine, api_steps, barrier)
+            del prob, local_prob, resident
+            torch.cuda.empty_cache()
+            extra["conv"] = conv_block(dev, engine)
     if world > 1:
         dist.barrier()
 
@@ -512,6 +515,56 @@ def cfg2_block(lib, dev, pk, engine, api_steps, barrier):
                 value=K_CG / (t_solve * 1e-3), unit=UNIT, ms_per_step=t_solve,
                 matvec=dict(us_per_product=1e3 * t_mv, tflops_algorithmic=f_mv / (t_mv * 1e-3) / 1e12),
                 roofline=roof, e2e_api=api)
+
+
+def build_allcnnc(classes=100, seed=0):
+    """All-CNN-C on a 3x32x32 input (the DeepOBS cifar100_allcnnc architecture of BASELINE.json configs[4], symmetric
+    padding, eval mode: no dropout)."""
+    nn = torch.nn
+    torch.manual_seed(seed)
+
+    def block(cin, cout, k, stride=1, pad=0):
+        return [nn.Conv2d(cin, cout, k, stride=stride, padding=pad), nn.ReLU()]
+    layers = (block(3, 96, 3, pad=1) + block(96, 96, 3, pad=1) + block(96, 96, 3, stride=2, pad=1) + block(96, 192, 3, pad=1)
+              + block(192, 192, 3, pad=1) + block(192, 192, 3, stride=2, pad=1) + block(192, 192, 3) + block(192, 192, 1)
+              + block(192, classes, 1) + [nn.AvgPool2d(6), nn.Flatten()])
+    return nn.Sequential(*layers)
+
+
+def conv_block(dev, engine, batch=1024):
+    """BASELINE.json configs[4] (first conv slice): All-CNN-C, CrossEntropy, one GPU's share (1024) of the 8192 batch:
+    time of one GGN-vector and one Hessian-vector product, each alone on the device.  F_Gv = 2N(4S - 2 m1),
+    F_Hv = 2N(6S - 4 m1) with S = 271 420 416 MAC/sample, m1 = 2 654 208."""
+    from pytorchhessianfree_b200.lowering import lower_module
+    from pytorchhessianfree_b200.native import NativeNet
+    from pytorchhessianfree_b200.problem import NativeProblem
+
+    S, m1 = 271420416, 2654208
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    model = build_allcnnc().to(dev)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    params = list(model.parameters())
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(batch, 3, 32, 32, generator=g).to(dev)
+    t = torch.randint(0, 100, (batch,), generator=g).to(dev)
+    prog = lower_module(model, loss_fn, params, input_shape=(3, 32, 32))
+    theta = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+    net = NativeNet(prog.layers, prog.loss, prog.reduction, prog.n_params, engine=engine)
+    out = dict(workload=f"allcnnc_3x32x32_cifar100_ce_batch{batch}_eval", params=theta.numel(), batch=batch)
+    v, res = torch.randn_like(theta), torch.empty_like(theta)
+    for curv, flops in (("ggn", 2.0 * batch * (4 * S - 2 * m1)), ("hessian", 2.0 * batch * (6 * S - 4 * m1))):
+        prob = NativeProblem(net, theta, curv, [(x, t)])
+        t_lin = _timed(prob.linearize, flush, reps=3)
+        if curv == "hessian":
+            prob.gradient()
+        t_mv = _timed(lambda: prob.matvec(v, res), flush, reps=5)
+        out[curv] = dict(ms_per_product=t_mv, products_per_s=1e3 / t_mv, tflops_algorithmic=flops / (t_mv * 1e-3) / 1e12,
+                         ms_linearise=t_lin, workspace_gib=sum(l.workspace.numel() for l in prob.mvp_lins) / 2 ** 30)
+        del prob
+        torch.cuda.empty_cache()
+    out["note"] = ("CPU reference (SURVEY.md section 6, 8 host cores, batch 64): 537 ms per _Gv, 1 282 ms per _Hv, i.e. 8.6 / 20.5 s at "
+                   "this batch if it scaled linearly")
+    return out
 
 
 def main():
