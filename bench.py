@@ -234,7 +234,7 @@ def run_native(args):
 
     def solve(prob, g, M):
         return pcg_device(prob.matvec, -g, minv=M.minv, damping=DAMPING, max_iter=K_CG, tol=0.0,
-                          martens_conv_crit=False, store_x_at_iters=None, poll=K_CG)
+                          martens_conv_crit=False, store_x_at_iters=None, poll=K_CG, out_buffer=prob.out_buffer())
 
     def barrier():
         if world > 1:
@@ -353,8 +353,28 @@ def run_native(args):
         e1.record()
         barrier()
         us = reduce_max(e0.elapsed_time(e1)) * 1e3 / 50
-        ar = dict(bytes=4 * P, us=us, bus_gbs=2.0 * (world - 1) / world * 4 * P / (us * 1e-6) / 1e9,
-                  note="NCCL all-reduce of the FP32 P-vector on the launching stream, back to back; reference 725 GB/s bus at 1 GiB")
+        ar = dict(bytes=4 * P, nccl_us=us, nccl_bus_gbs=2.0 * (world - 1) / world * 4 * P / (us * 1e-6) / 1e9,
+                  note="all-reduce of the FP32 P-vector on the launching stream, back to back: ncclAllReduce, and the "
+                       "switch-reduced kernel of this repository (hf_allreduce_multimem) the solve uses when the fabric has "
+                       "multicast; reference: 725 GB/s bus at 1 GiB")
+        from pytorchhessianfree_b200.dist import SymmetricVector
+        sv = SymmetricVector.try_create(P, dev, group, force=True)
+        ar["solve_uses"] = "multimem" if prob.out_buffer() is not None else "nccl"
+        if sv is not None:
+            sv.vec.copy_(buf)
+            for _ in range(5):
+                sv.all_reduce_()
+            barrier()
+            e0.record()
+            for _ in range(50):
+                sv.all_reduce_()
+            e1.record()
+            barrier()
+            us = reduce_max(e0.elapsed_time(e1)) * 1e3 / 50
+            ar.update(us=us, bus_gbs=2.0 * (world - 1) / world * 4 * P / (us * 1e-6) / 1e9)
+            sv.vec.zero_()
+        else:
+            ar.update(us=ar["nccl_us"], bus_gbs=ar["nccl_bus_gbs"])
 
     # ---- per-kernel rooflines and the round-1 workload, measured live (rank 0, kernels alone on the device) ----
     pk = peaks()

@@ -229,6 +229,21 @@ int hf_net_first_layer_span(const hf_net_t* net, int64_t* offset, int64_t* count
  * (preconditioners.py:11-60 incl. the rescaling at :56-58).                                  */
 int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t accumulate, void* stream);
 
+/* Tooling (tools/scale_probe.py): barrier flavour of hf_allreduce_multimem. bit 0: the entry barrier is a relaxed
+ * rendezvous; bit 1: no per-thread system fence in front of the exit barrier.  Default 3. */
+void hf_debug_allreduce_variant(int32_t v);
+
+/* ------------------------------------------------------------------------------------------
+ * The exchange step of the data-parallel path (new; the reference is single-device): in-place all-reduce(sum) of
+ * count floats at element `offset` of a SYMMETRIC buffer through the NVSwitch multicast address (multimem.ld_reduce /
+ * multimem.st, two-shot).  d_multicast: the multicast address of the buffer; d_signal_pads: device array of `world`
+ * pointers to the ranks' zero-initialised, peer-mapped signal pads (>= max_blocks * world uint32 each) -- both as
+ * torch.distributed._symmetric_memory hands them out.  offset % 4 == 0, count % (4 * world) == 0.  Every rank must make
+ * the same call; d_skip as in hf_ggn_matvec (the flag is replicated, so all ranks skip together).
+ * ------------------------------------------------------------------------------------------ */
+int hf_allreduce_multimem(void* d_multicast, void* d_signal_pads, int32_t rank, int32_t world, int64_t offset, int64_t count,
+                          int32_t max_blocks, const int32_t* d_skip, void* stream);
+
 /* device pointers into the linearisation, for tests: logits [batch,C] */
 const float* hf_lin_logits(const hf_lin_t* lin);
 

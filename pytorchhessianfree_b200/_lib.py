@@ -89,6 +89,8 @@ SIGNATURES = {
     "hf_matvec_phase": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "hf_net_first_layer_span": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "hf_lin_logits": (_vp, [_vp]),
+    "hf_allreduce_multimem": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _i64, _i32, _vp, _vp]),
+    "hf_debug_allreduce_variant": (None, [_i32]),
     "hf_contract_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "hf_contract": (C.c_int, [_i32, _i64, _i64, _i64, _i32, C.POINTER(Operand), C.POINTER(Operand), _vp, _i64, _vp, _sz,
                               _vp]),

@@ -211,7 +211,7 @@ def cg(
 
 
 def pcg_device(matvec, b, x0=None, minv=None, damping=0.0, max_iter=250, tol=1e-5, atol=None,
-               martens_conv_crit=True, store_x_at_iters=None, poll=3, verbose=False, use_graph=False):
+               martens_conv_crit=True, store_x_at_iters=None, poll=3, verbose=False, use_graph=False, out_buffer=None):
     """The same solve with a device-resident operator and **no host synchronisation per iteration**.
 
     ``matvec(v, out, skip_ptr)`` enqueues ``out = B v`` (the undamped curvature product) on the current
@@ -237,7 +237,9 @@ def pcg_device(matvec, b, x0=None, minv=None, damping=0.0, max_iter=250, tol=1e-
     max_iter = b.numel() if max_iter is None else int(max_iter)
     keep = set(cg_storing_grid(max_iter) if store_x_at_iters is None else store_x_at_iters)
     s = _Solver(b, max_iter)
-    Bp = torch.empty_like(b)
+    # `out_buffer`: where the operator wants its products written (a data-parallel problem hands out a view of its
+    # symmetric vector, so that the per-iteration all-reduce can run through the NVSwitch in place)
+    Bp = out_buffer if out_buffer is not None and out_buffer.shape == b.shape and out_buffer.dtype == b.dtype else torch.empty_like(b)
     if x0 is None:
         s.init(None, None, minv, damping, tol, atol, martens_conv_crit, False)
     else:

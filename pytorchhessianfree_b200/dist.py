@@ -49,3 +49,74 @@ def global_count(n_local, group=None, device=None):
     n = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
     all_reduce_sum(n, group)
     return int(n.item())
+
+
+# Whether the per-iteration exchange of the solve goes through hf_allreduce_multimem when the fabric allows it.  Off: on
+# the 8-GPU boxes measured so far the solve was FASTER with ncclAllReduce overlapped on a side stream (profiles/
+# r2_summary.md), although the kernel alone beats NCCL at this size.
+NVLS_DEFAULT = False
+
+
+class SymmetricVector:
+    """A flat FP32 vector in symmetric memory (same buffer on every rank of ``group``, peer-mapped, behind one NVSwitch
+    multicast address) with an in-place all-reduce(sum) through the switch: ``hf_allreduce_multimem`` (csrc/collective.cu,
+    hand-written ``multimem.ld_reduce`` / ``multimem.st``).  ``torch.distributed._symmetric_memory`` allocates the buffer
+    and exchanges the handles -- plumbing; the collective itself is this repository's kernel.  ``try_create`` returns None
+    when the process group, the driver or the fabric cannot provide a multicast mapping (the caller then keeps NCCL)."""
+
+    def __init__(self, numel, device, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.world = dist.get_world_size(group)
+        self.quantum = 4 * self.world  # float4 slices per rank
+        self.numel = int(numel)
+        padded = (self.numel + self.quantum - 1) // self.quantum * self.quantum
+        self.buf = symm_mem.empty(padded, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        if not self.hdl.multicast_ptr:
+            raise RuntimeError("no multicast mapping for the symmetric buffer")
+        self.rank = self.hdl.rank
+        self.max_blocks = max(1, min(64, self.hdl.signal_pad_size // (4 * self.world)))
+        self.vec = self.buf[: self.numel]
+        self.hdl.barrier()  # every rank has zeroed its buffer before anybody reduces
+
+    _cache = {}
+
+    @staticmethod
+    def try_create(numel, device, group, force=False):
+        """One symmetric vector per (group, length, device), created collectively on first use and shared by every
+        problem of the process afterwards (a rendezvous per optimizer step would cost more than it saves).
+        ``HF_NVLS=1`` / ``0`` switches the solver's use of it on / off (default: see NVLS_DEFAULT); ``force`` is for
+        callers that want the collective itself (tests, tools)."""
+        import os
+
+        import torch.distributed as dist
+
+        want = force or os.environ.get("HF_NVLS", "1" if NVLS_DEFAULT else "0") == "1"
+        if group is None or not want or dist.get_backend(group) != "nccl":
+            return None
+        key = (id(group), int(numel), str(device))
+        if key not in SymmetricVector._cache:
+            try:
+                SymmetricVector._cache[key] = SymmetricVector(numel, device, group)
+            except Exception:  # noqa: BLE001 -- no symmetric memory / multicast here: NCCL stays
+                SymmetricVector._cache[key] = None
+        return SymmetricVector._cache[key]
+
+    def padded_range(self, begin, end):
+        """[begin, end) of the vector widened to the collective's granularity (the padding holds zeros on every rank)."""
+        q = self.quantum
+        return begin // q * q, min(self.buf.numel(), (end + q - 1) // q * q)
+
+    def all_reduce_(self, begin=0, end=None, skip_ptr=None, stream=None):
+        """In-place sum over the ranks of elements [begin, end) (widened with ``padded_range``), on ``stream``."""
+        from . import _lib
+
+        lo, hi = self.padded_range(begin, self.numel if end is None else end)
+        _lib.check(self.lib.hf_allreduce_multimem(self.hdl.multicast_ptr, self.hdl.signal_pad_ptrs_dev, self.rank, self.world, lo, hi - lo,
+                                                  self.max_blocks, skip_ptr, stream if stream is not None else _lib.stream()))

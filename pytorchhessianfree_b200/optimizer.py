@@ -205,7 +205,7 @@ class HessianFree(torch.optim.Optimizer):
             x_iters, m_iters, cg_reason = pcg_device(
                 problem.matvec, b, x0=state["x0"], minv=None if M_func is None else M_func.minv, damping=damping,
                 max_iter=self._group["cg_max_iter"], martens_conv_crit=self.martens_conv_crit,
-                store_x_at_iters=grid, verbose=self.verbose)
+                store_x_at_iters=grid, verbose=self.verbose, out_buffer=problem.out_buffer())
         else:
             x_iters, m_iters, cg_reason = cg(
                 A=lambda x: mvp(x) + damping * x, b=b, x0=state["x0"], M=M_func, max_iter=self._group["cg_max_iter"],

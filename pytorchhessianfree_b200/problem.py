@@ -14,6 +14,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from .dist import SymmetricVector
 from .dist import all_reduce_sum as _all_reduce
 from .dist import global_count
 from .native import Linearization, NativeNet
@@ -44,6 +45,16 @@ class NativeProblem:
         # the overlap split needs the first layer's slice to be a 16-byte aligned prefix of the flat vector
         self._split_at = cnt if (off == 0 and 0 < cnt < theta.numel() and cnt % 4 == 0) else 0
         self._linearized = False
+        # The per-iteration exchange goes through the NVSwitch (hf_allreduce_multimem) when the curvature product can be
+        # written straight into a symmetric buffer (`out_buffer`); everything else (gradient, Fisher diagonal, candidate
+        # losses: once per step) stays on NCCL.
+        self._symm = SymmetricVector.try_create(theta.numel(), self.device, group) if theta.is_cuda else None
+        self._side = None
+
+    def out_buffer(self):
+        """Where the solver should let :meth:`matvec` write its products so that their all-reduce can run through the
+        switch: a view of the symmetric vector, or None (any tensor works then, over NCCL)."""
+        return self._symm.vec if self._symm is not None else None
 
     def _count(self, lins):
         return global_count(sum(l.n for l in lins), self.group, self.device)
@@ -94,6 +105,31 @@ class NativeProblem:
         all-reduce of the upper layers' slices (final after phase 0) overlaps with the first layer's weight
         gradient, the last and largest contraction of the sweep.  Both forms sum the same per-rank vectors with the
         same collective, so replicas stay bit-identical either way."""
+        nvls = self._symm is not None and out.data_ptr() == self._symm.vec.data_ptr()
+        if nvls and self.overlap_allreduce and len(self.mvp_lins) == 1 and self._split_at > 0:
+            # switch all-reduce of the upper layers' slices on a side stream, under the first layer's weight gradient
+            symm, lin = self._symm, self.mvp_lins[0]
+            cut = symm.padded_range(0, self._split_at)[1]  # >= the first layer's span: final after phase 0 from here on
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            lin.matvec_phase(self.curvature_opt, self.theta, v, out, 0, skip_ptr=skip_ptr)
+            self._side.wait_stream(main)
+            symm.all_reduce_(cut, symm.numel, skip_ptr, stream=self._side.cuda_stream)
+            lin.matvec_phase(self.curvature_opt, self.theta, v, out, 1, skip_ptr=skip_ptr)
+            main.wait_stream(self._side)
+            symm.all_reduce_(0, cut, skip_ptr)
+            return
+        if nvls:
+            if not self.mvp_lins:
+                out.zero_()
+            for i, lin in enumerate(self.mvp_lins):
+                if self.curvature_opt == "hessian":
+                    lin.hessian(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)
+                else:
+                    lin.ggn(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)
+            self._symm.all_reduce_(0, self._symm.numel, skip_ptr)
+            return
         if self.overlap_allreduce and self.group is not None and len(self.mvp_lins) == 1 and self._split_at > 0:
             import torch.distributed as dist
 
