@@ -95,49 +95,86 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """SM clock and clock-event (throttle) reasons of this rank's board while the timed region runs, every 50 ms.
+    Sampled by a thread of THIS process through NVML (the library nvidia-smi prints from), initialised before the
+    warm-up: a `nvidia-smi -lms` child per rank needs about a second to start on an 8-GPU box and holds driver locks
+    while it does, which inside a 0.3 s timed region slowed the very thing it was watching (profiles/r2_summary.md).
+    Falls back to that child, started at construction so that its start-up is over before the timed region, when the
+    NVML binding is missing.  Only samples taken between __enter__ and __exit__ count."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
-
-    def __enter__(self):
+        self.rows, self.proc, self.nvml, self.handle = [], None, None, None
+        self.live, self.stop, self.thread = False, False, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:  # noqa: BLE001 -- old torch / MIG naming: NVML order == CUDA order without a device mask
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+            self.source = "nvidia-smi"
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._pump, daemon=True)
+            except OSError:
+                self.proc = None
+        if self.thread:
             self.thread.start()
-        except OSError:
-            self.proc = None
-        return self
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop:
+            if self.live:
+                try:
+                    mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    self.rows.append((mhz, self.max_mhz, [name for name, bit in self.BITS if mask & bit]))
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.05 if self.live else 0.005)
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            if not self.live:
+                continue
+            c = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((float(c[0]), float(c[1]),
+                                  [name for (name, _), v in zip(self.BITS, c[3:7]) if v.lower().startswith("active")]))
+            except (ValueError, IndexError):
+                continue
+
+    def __enter__(self):
+        self.live = True
+        return self
 
     def __exit__(self, *a):
+        self.live, self.stop = False, True
         if self.proc:
             self.proc.terminate()
+        if self.thread:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+        sm = sorted(r[0] for r in self.rows)
+        mx = max((r[1] for r in self.rows), default=0.0)
+        reasons = sorted({name for r in self.rows for name in r[2]})
         busy = [v for v in sm if v > 0.5 * mx] or sm
-        return dict(sm_mhz=busy[len(busy) // 2] if busy else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
-                    samples=len(sm))
+        return dict(sm_mhz=busy[len(busy) // 2] if busy else None, sm_max_mhz=mx or None, reasons=reasons, samples=len(sm),
+                    source=self.source)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -248,13 +285,14 @@ def run_native(args):
         return float(t.item())
 
     # ---- device-resident arm: inputs in HBM, linearisation done, time the solves -------------------
+    clk = ClockSampler(local)  # initialised here, armed around the timed region
     prob, g, M = setup(resident, group)
     for _ in range(args.warmup):
         solve(prob, g, M)
     barrier()
     n0 = lib.hf_debug_launch_count()
     times = []
-    with ClockSampler(local) as clk:
+    with clk:
         for _ in range(args.steps):
             flush.fill_(1)
             barrier()

@@ -51,10 +51,10 @@ def global_count(n_local, group=None, device=None):
     return int(n.item())
 
 
-# Whether the per-iteration exchange of the solve goes through hf_allreduce_multimem when the fabric allows it.  Off: on
-# the 8-GPU boxes measured so far the solve was FASTER with ncclAllReduce overlapped on a side stream (profiles/
-# r2_summary.md), although the kernel alone beats NCCL at this size.
-NVLS_DEFAULT = False
+# Whether the per-iteration exchange of the solve goes through hf_allreduce_multimem when the fabric allows it (else, and
+# with HF_NVLS=0, ncclAllReduce): 8 B200, 11.3 MB vector: 41 us against 86 us alone, 786 against 754 products/s in the solve
+# (tools/scale_probe.py, profiles/r2_summary.md).
+NVLS_DEFAULT = True
 
 
 class SymmetricVector:
@@ -81,7 +81,8 @@ class SymmetricVector:
         if not self.hdl.multicast_ptr:
             raise RuntimeError("no multicast mapping for the symmetric buffer")
         self.rank = self.hdl.rank
-        self.max_blocks = max(1, min(64, self.hdl.signal_pad_size // (4 * self.world)))
+        # 8-16 CTAs of 512 threads keep the links busy; more only add contention (8: 40.8 us, 64: 45.8 us at 8 ranks)
+        self.max_blocks = max(1, min(16, self.hdl.signal_pad_size // (4 * self.world)))
         self.vec = self.buf[: self.numel]
         self.hdl.barrier()  # every rank has zeroed its buffer before anybody reduces
 

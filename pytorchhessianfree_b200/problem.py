@@ -36,11 +36,12 @@ class NativeProblem:
             else [net.linearize(x, t, loss_only=True) for x, t in loss_data]
         self.n_mvp, self.n_grad, self.n_loss = (self._count(l) for l in (self.mvp_lins, self.grad_lins, self.loss_lins))
         self._cand = torch.empty_like(theta)
-        # Overlap the all-reduce of the upper layers' slices with the first layer's weight gradient (see matvec).  Pays
-        # once the vector is large: measured on 8 B200 at P = 2.8 M (autoencoder) 697 vs 660 products/s, at P = 0.67 M
-        # (MLP) two collectives cost more fixed latency than the overlap hides.  HF_OVERLAP_ALLREDUCE=0/1 overrides.
-        env = os.environ.get("HF_OVERLAP_ALLREDUCE")
-        self.overlap_allreduce = (env == "1") if env in ("0", "1") else theta.numel() >= 2_000_000
+        # Overlapping the all-reduce of the upper layers' slices with the first layer's weight gradient (see matvec) is an
+        # option, off by default: timed in ONE process group on 8 B200 (tools/scale_probe.py, P = 2.8 M autoencoder) the
+        # in-line exchange won both on NCCL (754 vs 739 products/s) and through the switch (786 vs 774): the collective
+        # takes SMs and L2 bandwidth from the contraction it hides behind, and is two launches instead of one.
+        # HF_OVERLAP_ALLREDUCE=1 turns it on.
+        self.overlap_allreduce = os.environ.get("HF_OVERLAP_ALLREDUCE") == "1"
         off, cnt = net.first_layer_span()
         # the overlap split needs the first layer's slice to be a 16-byte aligned prefix of the flat vector
         self._split_at = cnt if (off == 0 and 0 < cnt < theta.numel() and cnt % 4 == 0) else 0
@@ -100,11 +101,12 @@ class NativeProblem:
     def matvec(self, v, out, skip_ptr=None):
         """``out = B v`` (no damping), enqueued without host synchronisation.
 
-        Data-parallel: one all-reduce(sum) of the flat vector after the local chunk sum.  With
-        ``overlap_allreduce`` (default for P >= 2 M) and one chunk per rank the sweep runs in two phases and the
-        all-reduce of the upper layers' slices (final after phase 0) overlaps with the first layer's weight
-        gradient, the last and largest contraction of the sweep.  Both forms sum the same per-rank vectors with the
-        same collective, so replicas stay bit-identical either way."""
+        Data-parallel: one all-reduce(sum) of the flat vector after the local chunk sum -- through the NVSwitch with this
+        library's own kernel (hf_allreduce_multimem) when ``out`` is :meth:`out_buffer`, else ncclAllReduce.  With
+        ``overlap_allreduce`` (opt-in) and one chunk per rank the sweep runs in two phases and the all-reduce of the
+        upper layers' slices (final after phase 0) overlaps with the first layer's weight gradient, the last and
+        largest contraction of the sweep.  Every form sums the same per-rank vectors once per element and hands every
+        rank the same bits, so replicas stay bit-identical."""
         nvls = self._symm is not None and out.data_ptr() == self._symm.vec.data_ptr()
         if nvls and self.overlap_allreduce and len(self.mvp_lins) == 1 and self._split_at > 0:
             # switch all-reduce of the upper layers' slices on a side stream, under the first layer's weight gradient

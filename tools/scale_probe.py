@@ -70,7 +70,7 @@ def main():
         say("no multicast mapping: nothing else to compare")
     else:
         say(f"signal pad {sv.hdl.signal_pad_size} B -> at most {sv.max_blocks} CTAs")
-        cap = sv.max_blocks
+        cap = max(1, min(64, sv.hdl.signal_pad_size // (4 * world)))
         for variant in (0, 1, 2, 3):
             lib.hf_debug_allreduce_variant(variant)
             floor = 1e3 * timed(lambda: sv.all_reduce_(0, sv.quantum), 50)
