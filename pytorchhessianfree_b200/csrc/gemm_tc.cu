@@ -394,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
     tc_mark(5, threadIdx.x == 0, p.trace_epoch);
     float cs[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of what this lane stores (bias gradient of the next layer)
-    epilogue_dispatch<LDS_ROW>(g, stage, lane * 4, m0 + warp * 32, n0 + lane * 4, cs);
+    epilogue_dispatch<LDS_ROW>(g, stage, lane * 4, m0 + warp * 32, n0 + lane * 4, cs, blockIdx.z);
     if (g.colpart) {
       // 4 warps x 32 rows -> one row of column sums per CTA, fixed order (deterministic)
       float* red = reinterpret_cast<float*>(tiles) + 4 * 32 * (BN + 4);

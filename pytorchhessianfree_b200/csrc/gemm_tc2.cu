@@ -35,17 +35,15 @@ namespace hf {
 constexpr int P2_ROWS = 128;                    // rows of A, and of B, one CTA stages
 constexpr int P2_TILE = 256;                    // pair tile: 256 x 256
 constexpr int P2_STAGES = 3;
-constexpr int P2_THREADS = 192;
+constexpr int P2_THREADS = 320;                 // one-tile kernel: 8 epilogue warps + producer + MMA issuer
+constexpr int P2P_THREADS = 192;                // persistent kernel: 4 epilogue warps + producer + MMA issuer
 constexpr int P2_LDS_ROW = 128 + 4;             // staged accumulator rows, 128 columns per pass: 4 warps x 32 rows x 132 floats = 66 KB
 
-// Two builds of the same kernel, by k-block width BK (floats of K per pipeline stage):
-//   BK = 32: 64 KB per stage, 193 KB per CTA, ONE CTA per SM (the default).  Three stages hide the L2 latency of a lone
-//            CTA: with L2-resident operands the main loop runs at the MMA floor (0.50-0.60 us per k-block,
-//            tools/tc2_slope.py).  Everything outside the loop is exposed: per 128x256 CTA tile ~3.3 us of prologue and
-//            pipeline fill and ~7.4 us of epilogue (tools/tc2_trace.py).
-//   BK = 16: 32 KB per stage, 97 KB per CTA, TWO CTAs per SM (two pairs per TPC, 2 x 256 TMEM columns); HF_TC2_BK=16.
-//            Parity-green; meant to run one pair's epilogue under the other pair's main loop, but co-resident pairs of one
-//            launch run in lockstep, so it measures the same as BK = 32.  Kept for the persistent variant that staggers them.
+// Stage geometry by k-block width BK (floats of K per pipeline stage).  The one-tile kernel runs BK = 32: 64 KB per
+// stage, 193 KB per CTA, ONE CTA per SM; three stages hide the L2 latency of a lone CTA: with L2-resident operands the
+// main loop runs at the MMA floor (0.50-0.60 us per k-block, tools/tc2_slope.py).  (A BK = 16 build with two CTAs per
+// SM -- two pairs per TPC, 2 x 256 TMEM columns -- measured the same, 55 vs 53 us: co-resident pairs of one launch run
+// in lockstep, so nothing overlapped; removed.)  BK = 16 survives as an option of the persistent kernel below.
 template <int BK>
 struct P2Cfg {
   static constexpr int OP32 = P2_ROWS * BK * 4;   // FP32 tile of one operand
@@ -53,8 +51,6 @@ struct P2Cfg {
   static constexpr int A32 = 0, AHI = OP32, ALO = OP32 + OP16, B32 = OP32 + 2 * OP16, BHI = B32 + OP32, BLO = BHI + OP16;
   static constexpr int STAGE_BYTES = 2 * (OP32 + 2 * OP16);  // 64 KB / 32 KB
   static constexpr int SMEM = P2_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int CTAS_PER_SM = BK == 32 ? 1 : 2;
-  static_assert(4 * 32 * P2_LDS_ROW * 4 + 4 * P2_TILE * 4 <= P2_STAGES * STAGE_BYTES, "epilogue staging must fit in the idle ring");
 };
 
 // UMMA descriptors of the operand tiles of one stage, k-step ks (one MMA: 8 floats / 16 bf16 of K).
@@ -114,9 +110,10 @@ __device__ __forceinline__ void load_operand(uint32_t dst32, uint32_t dst_hi, ui
 }
 
 template <int BK>
-__global__ void __launch_bounds__(P2_THREADS, P2Cfg<BK>::CTAS_PER_SM)
+__global__ void __launch_bounds__(P2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc2Args p) {
   using Cfg = P2Cfg<BK>;
+  static_assert(8 * 32 * P2_LDS_ROW * 4 + 4 * P2_TILE * 4 <= P2_STAGES * Cfg::STAGE_BYTES, "epilogue staging must fit in the idle ring");
   const GemmArgs& g = p.g;
   if (g.skip && *g.skip) return;  // uniform across the pair: solver already terminated
   const uint32_t rank = cluster_ctarank();  // 0 = leader: issues the MMAs for both CTAs
@@ -201,54 +198,280 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc
       umma2_commit(acc_full);
     }
   } else {
-    // ---------------- epilogue (both CTAs: 128 rows x 256 columns each) ----------------
+    // ---------------- epilogue (both CTAs: 128 rows x 256 columns each; warps 0-3 and 6-9) ----------------
     // TMEM -> registers (one accumulator row per lane) -> shared (the ring is idle once acc_full fired: every MMA of
-    // the pair has retired and every TMA box was consumed) -> row-wise coalesced fused epilogue; 128 columns per pass.
+    // the pair has retired and every TMA box was consumed) -> row-wise coalesced fused epilogue.  A warp reads the TMEM
+    // lane quarter (warp % 4); two warps share a quarter and take 128 columns each: the chain tcgen05.ld -> st.shared ->
+    // ld.shared -> (loads of the fused terms) -> st.global is latency-bound with one warp per scheduler (4 warps: 7.4 us
+    // for the 128 KB of a CTA, tools/tc2_trace.py), so the second set of warps nearly halves it.
     if (total > 0) {
       mbar_wait(acc_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     tc2_mark(3, threadIdx.x == 0);
-    const uint32_t stage = smem_u32(tiles) + warp * 32 * P2_LDS_ROW * 4;
-    float cs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // column sums of what this lane stores
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    const int q = warp & 3, h = warp >= 6 ? 1 : 0;
+    const uint32_t stage = smem_u32(tiles) + (h * 4 + q) * 32 * P2_LDS_ROW * 4;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of what this lane stores
 #pragma unroll 2
-      for (int c = 0; c < 128; c += 16) {
-        float v[16];
-        if (total > 0) {
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + h * 128 + c, v);
-        } else {
+    for (int c = 0; c < 128; c += 16) {
+      float v[16];
+      if (total > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + h * 128 + c, v);
+      } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + (lane * P2_LDS_ROW + c + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
-      __syncwarp();
-      if (h == 0) tc2_mark(4, threadIdx.x == 0);
-      epilogue_dispatch<P2_LDS_ROW>(g, stage, lane * 4, m0 + warp * 32, n0 + h * 128 + lane * 4, cs[h]);
-      __syncwarp();  // the warp's staging rows are rewritten by the next pass
-      tc2_mark(5 + h, threadIdx.x == 0);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + (lane * P2_LDS_ROW + c + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
     }
+    __syncwarp();
+    tc2_mark(4, threadIdx.x == 0);
+    epilogue_dispatch<P2_LDS_ROW>(g, stage, lane * 4, m0 + q * 32, n0 + h * 128 + lane * 4, cs, blockIdx.z);
+    tc2_mark(5 + h, lane == 0 && q == 0);
     if (g.colpart && m0 < g.M) {  // (the grid is padded to whole pairs: a CTA entirely below the matrix owns no row of colpart)
-      // 4 warps x 32 rows -> one row of column sums per CTA (= per 128-row block, like gemm_tc.cu), fixed order
-      float* red = reinterpret_cast<float*>(tiles) + 4 * 32 * P2_LDS_ROW;
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        *reinterpret_cast<float4*>(red + warp * P2_TILE + h * 128 + lane * 4) = make_float4(cs[h][0], cs[h][1], cs[h][2], cs[h][3]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int idx = threadIdx.x; idx < P2_TILE; idx += 128) {
-        const float t = (red[idx] + red[P2_TILE + idx]) + (red[2 * P2_TILE + idx] + red[3 * P2_TILE + idx]);
-        if (n0 + idx < g.N) g.colpart[(int64_t)blockIdx.x * g.N + n0 + idx] = t;
-      }
+      // 4 quarters x 32 rows -> one row of column sums per CTA (= per 128-row block, like gemm_tc.cu), fixed order
+      float* red = reinterpret_cast<float*>(tiles) + 8 * 32 * P2_LDS_ROW;
+      *reinterpret_cast<float4*>(red + q * P2_TILE + h * 128 + lane * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int idx = (h * 4 + q) * 32 + lane;  // one column per epilogue thread
+      const float t = (red[idx] + red[P2_TILE + idx]) + (red[2 * P2_TILE + idx] + red[3 * P2_TILE + idx]);
+      if (n0 + idx < g.N) g.colpart[(int64_t)blockIdx.x * g.N + n0 + idx] = t;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();  // neither CTA leaves (or frees TMEM, or lets its shared memory go) while the pair is in flight
   tc2_mark(7, threadIdx.x == 0);
   if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(P2_TILE) : "memory");
+}
+
+// ---- persistent variant -------------------------------------------------------------------------------
+// Same tiles, same operand forms, same epilogue; what changes is what happens BETWEEN the tiles of a launch that has
+// more pair tiles than the machine has pairs (the 7500-row contractions of the autoencoder: 120 tiles on 74 pairs).
+// tools/tc2_trace.py: of the 31 us a pair spends on one such tile, 11 us are outside the main loop (prologue 1.3 us,
+// pipeline fill 2 us, epilogue 7.4 us during which 148 CTAs store 128 KB each and nothing computes), and the second
+// wave pays them again.  Here one pair per SM pair stays resident and walks the tile list:
+//   * the accumulator is double-buffered in TMEM (2 x 256 columns = all of it): the MMA warp starts tile i+1 in the
+//     other buffer as soon as its operands land, while warps 0-3 drain tile i;
+//   * the epilogue stages through its OWN shared memory, not through the idle ring, so the producer keeps prefetching.
+//     A first cut kept the 128-column passes (66 KB of staging) and paid for them with the ring (128 KB: 2 x 64 KB or
+//     4 x 32 KB): parity-green and SLOWER than the one-tile kernel on two-wave shapes (62.8-69.4 vs 57.2 us on 7500 x
+//     1000 x 784) -- the main loop lost more to the shallow ring than the overlap won.  So: passes of 32 columns (18 KB
+//     of staging: 4 warps x 32 rows x 36 floats), four accumulator rows in flight per warp instruction (each lane
+//     quarter stores 128 contiguous bytes of a row), and the full 192 KB ring of the one-tile kernel;
+//   * barriers, TMEM allocation and the cluster rendezvous happen once per launch.
+// acc_full[b]  : leader's MMA thread -> epilogue warps of both CTAs (tcgen05.commit, multicast)
+// acc_empty[b] : 4 epilogue warps x 2 CTAs -> leader's MMA thread (remote mbarrier arrive), after their last tcgen05.ld
+constexpr int P2_COLS_P = 32;  // columns per epilogue pass of the persistent kernel
+template <int BK>
+struct P2PCfg {
+  static constexpr int STAGES = BK == 32 ? 3 : 6;
+  static constexpr int STAGE_BYTES = P2Cfg<BK>::STAGE_BYTES;
+  static constexpr int RING = STAGES * STAGE_BYTES;
+  static constexpr int COLS = P2_COLS_P;
+  static constexpr int LDS_ROW = COLS + 4;  // 144-byte rows: quarter-warp stores / loads hit 8 distinct 16-byte bank groups
+  static constexpr int STAGING = 4 * 32 * LDS_ROW * 4;
+  static constexpr int RED = 4 * P2_TILE * 4;
+  static constexpr int SMEM = RING + STAGING + RED + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 227 * 1024, "persistent pair kernel: shared memory");
+};
+
+// One epilogue pass as a real call: inlined into the tile loop, the 40 specialisations of the row loop have their
+// loop-invariant setup hoisted above it and the kernel spills at 255 registers; behind a call it needs 100.
+template <int EPI>
+__device__ __noinline__ void tc2p_epilogue_kind(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, float* cs_out, int kz, int row_first) {
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (EPI == EPI_STORE)
+    epilogue_vec<EPI_STORE, HF_ACT_NONE, P2_COLS_P + 4>(g, stage, col, m_base, n, cs, kz, row_first, 4);
+  else
+    epilogue_act<EPI, P2_COLS_P + 4>(g, stage, col, m_base, n, cs, kz, row_first, 4);
+  cs_out[0] = cs[0], cs_out[1] = cs[1], cs_out[2] = cs[2], cs_out[3] = cs[3];
+}
+__device__ __forceinline__ void tc2p_epilogue_pass(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, float* cs, int kz, int row_first) {
+  switch (g.epi) {
+    case EPI_STORE: tc2p_epilogue_kind<EPI_STORE>(g, stage, col, m_base, n, cs, kz, row_first); break;
+    case EPI_BIAS_ACT: tc2p_epilogue_kind<EPI_BIAS_ACT>(g, stage, col, m_base, n, cs, kz, row_first); break;
+    case EPI_BIAS_DACT: tc2p_epilogue_kind<EPI_BIAS_DACT>(g, stage, col, m_base, n, cs, kz, row_first); break;
+    case EPI_DACT: tc2p_epilogue_kind<EPI_DACT>(g, stage, col, m_base, n, cs, kz, row_first); break;
+    default: tc2p_epilogue_kind<EPI_DACT_H>(g, stage, col, m_base, n, cs, kz, row_first); break;
+  }
+}
+
+struct Tc2Tiles {
+  int tiles_m, tiles_n, n_tiles;  // pair tiles along M, along N, in all (x split_k)
+};
+
+template <int BK>
+__global__ void __launch_bounds__(P2P_THREADS, 1)
+gemm_tc2p_kernel(const __grid_constant__ Tc2Maps maps, const __grid_constant__ Tc2Args p, const __grid_constant__ Tc2Tiles tl) {
+  using Cfg = P2Cfg<BK>;
+  using PC = P2PCfg<BK>;
+  constexpr int S = PC::STAGES;
+  const GemmArgs& g = p.g;
+  if (g.skip && *g.skip) return;
+  const uint32_t rank = cluster_ctarank();
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = tiles + PC::RING;
+  float* red = reinterpret_cast<float*>(staging + PC::STAGING);
+  uint64_t* bars = (uint64_t*)(staging + PC::STAGING + PC::RED);
+  uint64_t* full = bars;             // [S] leader's
+  uint64_t* empty = bars + S;        // [S] both (commit multicast)
+  uint64_t* acc_full = bars + 2 * S; // [2] both (commit multicast)
+  uint64_t* acc_empty = acc_full + 2;  // [2] leader's: 8 arrivals
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  tc2_mark(0, threadIdx.x == 0);
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 12; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i / 6][(i / 3) % 2][i % 3]) : "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * P2_TILE) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  tc2_mark(1, threadIdx.x == 0);
+
+  // tile t -> (pair-row block, column tile, K split); the same order the one-tile kernel's grid is rasterised in
+  auto n_kb_of = [&](int z) {
+    const int k_begin = z * g.k_per_split, k_end = min(g.K, k_begin + g.k_per_split);
+    return k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
+  };
+
+  if (warp == 4) {
+    // ---------------- TMA producer (both CTAs) ----------------
+    if (lane == 0) {
+      const uint32_t bar0 = map_to_cta(&full[0], 0);
+      int it = 0;
+      for (int t = cid; t < tl.n_tiles; t += n_clusters) {
+        const int xm = t % tl.tiles_m, yn = (t / tl.tiles_m) % tl.tiles_n, z = t / (tl.tiles_m * tl.tiles_n);
+        const int m0 = (2 * xm + (int)rank) * P2_ROWS, nb0 = yn * P2_TILE + (int)rank * P2_ROWS;
+        const int k_begin = z * g.k_per_split, n_kb = n_kb_of(z), total = n_kb * g.n_pairs;
+        for (int i = 0; i < total; ++i, ++it) {
+          const int s = it % S, ph = (it / S) & 1;
+          const int pr = i / n_kb, k0 = k_begin + (i % n_kb) * BK;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+          const uint32_t bar = bar0 + s * 8;
+          const uint32_t base = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+          load_operand<BK>(base + Cfg::A32, base + Cfg::AHI, base + Cfg::ALO, maps.m[pr][0], p.a_mn[pr], m0, k0, bar);
+          load_operand<BK>(base + Cfg::B32, base + Cfg::BHI, base + Cfg::BLO, maps.m[pr][1], p.b_mn[pr], nb0, k0, bar);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------- MMA issuer (leader CTA) ----------------
+    if (lane == 0 && rank == 0) {
+      int it = 0, lt = 0;
+      for (int t = cid; t < tl.n_tiles; t += n_clusters, ++lt) {
+        const int z = t / (tl.tiles_m * tl.tiles_n);
+        const int n_kb = n_kb_of(z), total = n_kb * g.n_pairs;
+        const int b = lt & 1;
+        mbar_wait_cluster(&acc_empty[b], ((lt >> 1) & 1) ^ 1);  // both CTAs have drained what this buffer held two tiles ago
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + b * P2_TILE;
+        for (int i = 0; i < total; ++i, ++it) {
+          const int s = it % S, ph = (it / S) & 1, pr = i / n_kb;
+          mbar_wait(&full[s], ph);
+          if (it == 0) tc2_mark(2, true);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int a_mn = p.a_mn[pr], b_mn = p.b_mn[pr];
+          const uint32_t idesc32 = umma_idesc(2u, a_mn, b_mn, P2_TILE, P2_TILE), idesc16 = umma_idesc(1u, a_mn, b_mn, P2_TILE, P2_TILE);
+          const uint32_t base = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks)
+            umma2_tf32(acc, desc32<BK>(base + Cfg::A32, a_mn, ks), desc32<BK>(base + Cfg::B32, b_mn, ks), idesc32, (i | ks) != 0);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            umma2_bf16(acc, desc16<BK>(base + Cfg::ALO, a_mn, ks), desc16<BK>(base + Cfg::BHI, b_mn, ks), idesc16, 1);
+            umma2_bf16(acc, desc16<BK>(base + Cfg::AHI, a_mn, ks), desc16<BK>(base + Cfg::BLO, b_mn, ks), idesc16, 1);
+          }
+          umma2_commit(&empty[s]);
+        }
+        umma2_commit(&acc_full[b]);
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs: 128 rows x 256 columns of every tile of the pair) ----------------
+    constexpr int COLS = PC::COLS, LDS = PC::LDS_ROW, PASSES = P2_TILE / COLS;
+    const uint32_t stage = smem_u32(staging) + warp * 32 * LDS * 4;
+    const int sub = lane >> 3, col = (lane & 7) * 4;  // row residue (mod 4) and first column of this lane within a pass
+    int lt = 0;
+    for (int t = cid; t < tl.n_tiles; t += n_clusters, ++lt) {
+      const int xm = t % tl.tiles_m, yn = (t / tl.tiles_m) % tl.tiles_n, z = t / (tl.tiles_m * tl.tiles_n);
+      const int mb = 2 * xm + (int)rank;  // 128-row block of this CTA
+      const int m0 = mb * P2_ROWS, n0 = yn * P2_TILE;
+      const int total = n_kb_of(z) * g.n_pairs;
+      const int b = lt & 1;
+      mbar_wait(&acc_full[b], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lt == 0) tc2_mark(3, threadIdx.x == 0);
+#pragma unroll 1
+      for (int h = 0; h < PASSES; ++h) {
+        float cs[4];
+#pragma unroll
+        for (int c = 0; c < COLS; c += 16) {
+          float v[16];
+          if (total > 0) {
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + b * P2_TILE + h * COLS + c, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + (lane * LDS + c + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+        }
+        if (h == PASSES - 1) {  // this warp has read the last of buffer b: hand it back before the last stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&acc_empty[b], 0);
+        }
+        __syncwarp();
+        tc2p_epilogue_pass(g, stage, col, m0 + warp * 32, n0 + h * COLS + col, cs, z, sub);
+        __syncwarp();
+        if (g.colpart) {  // column sums of the warp's 32 rows: the four row residues, fixed order
+          float4 v = make_float4(cs[0], cs[1], cs[2], cs[3]);
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, o), v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+            v.z += __shfl_xor_sync(0xffffffffu, v.z, o), v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+          }
+          if (sub == 0) *reinterpret_cast<float4*>(red + warp * P2_TILE + h * COLS + col) = v;
+        }
+      }
+      if (g.colpart) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (m0 < g.M)
+          for (int idx = threadIdx.x; idx < P2_TILE; idx += 128) {
+            const float tsum = (red[idx] + red[P2_TILE + idx]) + (red[2 * P2_TILE + idx] + red[3 * P2_TILE + idx]);
+            if (n0 + idx < g.N) g.colpart[(int64_t)mb * g.N + n0 + idx] = tsum;
+          }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // `red` is rewritten by the next tile
+      }
+      if (lt == 0) tc2_mark(6, threadIdx.x == 0);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  tc2_mark(7, threadIdx.x == 0);
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * P2_TILE) : "memory");
 }
 
 // ---- split-precision images ----------------------------------------------------------------------------
@@ -382,12 +605,35 @@ static int launch_bk(const Tc2Maps& maps, const Tc2Args& p, dim3 grid, cudaStrea
   return HF_OK;
 }
 
-// k-block width of a launch.  BK = 32 (one CTA per SM) unless HF_TC2_BK=16 asks for the co-resident build: measured on
-// B200 (tools/tc2_trace.py, 7500x1000x784) the two give the same time, 53 vs 55 us -- co-resident pairs start together,
-// share the tensor pipe at half rate each, reach their epilogues together, and nothing overlaps.
-int tc2_block_k(int, int, int) {
-  static const int forced = getenv("HF_TC2_BK") ? atoi(getenv("HF_TC2_BK")) : 0;
-  return forced == 16 ? 16 : 32;
+template <int BK>
+static int launch_persistent(const Tc2Maps& maps, const Tc2Args& p, const Tc2Tiles& tl, int n_clusters, cudaStream_t stream) {
+  static bool seen[64] = {};
+  if (first_use_on_device(seen))
+    HF_CUDA(cudaFuncSetAttribute(gemm_tc2p_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2PCfg<BK>::SMEM));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * n_clusters), cfg.blockDim = dim3(P2P_THREADS), cfg.dynamicSmemBytes = P2PCfg<BK>::SMEM, cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  HF_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2p_kernel<BK>, maps, p, tl));
+  note_launch();
+  return HF_OK;
+}
+
+// HF_TC2_PERSIST: 0 = one tile per pair always, 1 (default) = the persistent kernel when a launch has at least four
+// waves of pair tiles, 2 = always.  Measured (tools/tc_microbench.py): 60000 x 1000 x 784 (12.7 waves) 395 vs 451 us,
+// 8192 x 8192 x 2048 (13.8 waves) 957 vs 1019 us, but 7500 x 1000 x 784 (1.6 waves) 63.9 vs 57.5 us: while the epilogue
+// of tile i runs, the main loop of tile i+1 crawls (both live on shared-memory bandwidth: the MMAs read ~90 B/cycle of
+// operands, the epilogue stages 256 KB per tile through it), so with two tiles per pair the overlap buys less than
+// the narrower passes cost.  HF_TC2P_BK = 16 selects a six-stage / 16-wide ring (slower everywhere measured).
+static int tc2_persist_mode() {
+  static const int mode = getenv("HF_TC2_PERSIST") ? atoi(getenv("HF_TC2_PERSIST")) : 1;
+  return mode;
+}
+static int tc2p_block_k() {
+  static const int bk = getenv("HF_TC2P_BK") ? atoi(getenv("HF_TC2P_BK")) : 32;
+  return bk == 16 ? 16 : 32;
 }
 
 int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t stream) {
@@ -398,7 +644,12 @@ int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t stream) {
   if (g.split_k < 1) g.split_k = 1;
   if (g.split_k == 1) g.k_per_split = ((g.K + BKT - 1) / BKT) * BKT;
   HF_REQUIRE(g.k_per_split % BKT == 0, HF_ERR_INVALID, "tcgen05 engine: K split must be a multiple of %d", BKT);
-  const int bk = tc2_block_k(g.M, g.N, g.split_k);
+  Tc2Tiles tl;
+  tl.tiles_m = (g.M + P2_TILE - 1) / P2_TILE, tl.tiles_n = (g.N + P2_TILE - 1) / P2_TILE;
+  tl.n_tiles = tl.tiles_m * tl.tiles_n * g.split_k;
+  const int hw_pairs = std::max(1, sm_count() / 2);
+  const bool persistent = tc2_persist_mode() == 2 || (tc2_persist_mode() == 1 && tl.n_tiles >= 4 * hw_pairs);
+  const int bk = persistent ? tc2p_block_k() : 32;
   Tc2Maps maps;
   for (int s = 0; s < 2; ++s) {
     const int src = s < g.n_pairs ? s : 0;
@@ -408,8 +659,12 @@ int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t stream) {
     rc = operand_maps(maps.m[s][1], g.B[src], g.N, g.K, bk);
     if (rc) return rc;
   }
+  if (persistent) {
+    const int n_clusters = std::min(tl.n_tiles, hw_pairs);
+    return bk == 32 ? launch_persistent<32>(maps, p, tl, n_clusters, stream) : launch_persistent<16>(maps, p, tl, n_clusters, stream);
+  }
   const dim3 grid(2 * ((g.M + P2_TILE - 1) / P2_TILE), (g.N + P2_TILE - 1) / P2_TILE, g.split_k);
-  return bk == 32 ? launch_bk<32>(maps, p, grid, stream) : launch_bk<16>(maps, p, grid, stream);
+  return launch_bk<32>(maps, p, grid, stream);
 }
 
 }  // namespace hf

@@ -261,15 +261,17 @@ __device__ __forceinline__ void st4_image(const Image16& im, int64_t m, int n, i
 }
 
 // rows [m_base, m_base+32) x columns [n, n+4) of the tile; `stage` holds the warp's 32 accumulator rows with a pitch
-// of LDS_ROW floats, and this lane's four columns start `col` floats into each row
+// of LDS_ROW floats, and this lane's four columns start `col` floats into each row.  The lane visits rows row_first,
+// row_first + row_step, ...: (0, 1) when the 32 lanes span 128 columns of one row at a time, (lane / 8, 4) when a pass
+// is 32 columns wide and four rows are in flight per warp instruction (the persistent pair kernel's small staging).
 template <int EPI, int ACT, bool VEC, int LDS_ROW>
 __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, int cnt,
-                                              float (&cs)[4]) {
+                                              float (&cs)[4], int kz, int row_first, int row_step) {
   constexpr bool NEED_AUX = ACT != HF_ACT_NONE && EPI >= EPI_BIAS_DACT;
   // Every field is copied into a register first: `g` lives in the kernel-parameter window and is read through a
   // generic pointer, which the compiler must otherwise re-load after every global store (possible aliasing).
   const int64_t ldc = g.ldc, ldaux = g.ldaux;
-  float* const C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0) + n;
+  float* const C = g.C + (g.split_k > 1 ? (int64_t)kz * g.M * g.ldc : 0) + n;
   float* const C2 = g.C2 ? g.C2 + n : nullptr;
   const float* const aux = g.aux ? g.aux + n : nullptr;
   const float* const hga = g.h_ga ? g.h_ga + n : nullptr;
@@ -282,11 +284,11 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t stage,
   constexpr int RB = 4;  // rows in flight: their global loads are all issued before the first use
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // column sums in registers (`cs` is memory: it crosses a call boundary)
 #pragma unroll 1
-  for (int r0 = 0; r0 < rows; r0 += RB) {
+  for (int r0 = 0; r0 * row_step + row_first < rows; r0 += RB) {
     float x[RB][4], au[RB][4], ga[RB][4], rz[RB][4];
 #pragma unroll
     for (int j = 0; j < RB; ++j) {
-      const int r = min(r0 + j, rows - 1);  // clamp: tail slots re-read the last row and are not stored
+      const int r = min((r0 + j) * row_step + row_first, rows - 1);  // clamp: tail slots re-read the last row and are not stored
       const int64_t m = m_base + r;
       float4 t;  // explicit shared-space load (the pointer's address space is not visible to the compiler here)
       asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(stage + (r * LDS_ROW + col) * 4));
@@ -299,8 +301,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t stage,
     }
 #pragma unroll
     for (int j = 0; j < RB; ++j) {
-      if (r0 + j >= rows) break;
-      const int64_t m = m_base + r0 + j;
+      if ((r0 + j) * row_step + row_first >= rows) break;
+      const int64_t m = m_base + (r0 + j) * row_step + row_first;
       if (EPI == EPI_STORE) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) x[j][e] = alpha * x[j][e] + bi[e];
@@ -341,26 +343,26 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t stage,
 }
 
 template <int EPI, int ACT, int LDS_ROW>
-__device__ __forceinline__ void epilogue_vec(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, float (&cs)[4]) {
+__device__ __forceinline__ void epilogue_vec(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, float (&cs)[4], int kz, int row_first, int row_step) {
   const int cnt = min(4, g.N - n);
   if (cnt <= 0 || m_base >= g.M) return;
-  float* C = g.C + (g.split_k > 1 ? (int64_t)blockIdx.z * g.M * g.ldc : 0);
+  float* C = g.C + (g.split_k > 1 ? (int64_t)kz * g.M * g.ldc : 0);
   const bool al16 = ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(g.C2) | reinterpret_cast<uintptr_t>(g.aux) |
                       reinterpret_cast<uintptr_t>(g.h_ga) | reinterpret_cast<uintptr_t>(g.h_rz) |
                       reinterpret_cast<uintptr_t>(g.bias)) & 15u) == 0 && g.ldc % 4 == 0 && g.ldaux % 4 == 0;
   if (al16 && cnt == 4)
-    epilogue_rows<EPI, ACT, true, LDS_ROW>(g, stage, col, m_base, n, cnt, cs);
+    epilogue_rows<EPI, ACT, true, LDS_ROW>(g, stage, col, m_base, n, cnt, cs, kz, row_first, row_step);
   else
-    epilogue_rows<EPI, ACT, false, LDS_ROW>(g, stage, col, m_base, n, cnt, cs);
+    epilogue_rows<EPI, ACT, false, LDS_ROW>(g, stage, col, m_base, n, cnt, cs, kz, row_first, row_step);
 }
 
 template <int EPI, int LDS_ROW>
-__device__ __forceinline__ void epilogue_act(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, float (&cs)[4]) {
+__device__ __forceinline__ void epilogue_act(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, float (&cs)[4], int kz, int row_first, int row_step) {
   switch (g.act) {
-    case HF_ACT_RELU: epilogue_vec<EPI, HF_ACT_RELU, LDS_ROW>(g, stage, col, m_base, n, cs); break;
-    case HF_ACT_SIGMOID: epilogue_vec<EPI, HF_ACT_SIGMOID, LDS_ROW>(g, stage, col, m_base, n, cs); break;
-    case HF_ACT_TANH: epilogue_vec<EPI, HF_ACT_TANH, LDS_ROW>(g, stage, col, m_base, n, cs); break;
-    default: epilogue_vec<EPI, HF_ACT_NONE, LDS_ROW>(g, stage, col, m_base, n, cs); break;
+    case HF_ACT_RELU: epilogue_vec<EPI, HF_ACT_RELU, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
+    case HF_ACT_SIGMOID: epilogue_vec<EPI, HF_ACT_SIGMOID, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
+    case HF_ACT_TANH: epilogue_vec<EPI, HF_ACT_TANH, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
+    default: epilogue_vec<EPI, HF_ACT_NONE, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
   }
 }
 
@@ -368,13 +370,14 @@ __device__ __forceinline__ void epilogue_act(const GemmArgs& g, uint32_t stage, 
 // lane's four columns `col`..`col`+3 of the staged rows = global columns n..n+3.  Adds the column sums of what the lane
 // stored to cs (bias gradient of the layer below).
 template <int LDS_ROW>
-__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, float (&cs)[4]) {
+__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, uint32_t stage, int col, int m_base, int n, float (&cs)[4], int kz, int row_first = 0,
+                                                  int row_step = 1) {
   switch (g.epi) {
-    case EPI_STORE: epilogue_vec<EPI_STORE, HF_ACT_NONE, LDS_ROW>(g, stage, col, m_base, n, cs); break;
-    case EPI_BIAS_ACT: epilogue_act<EPI_BIAS_ACT, LDS_ROW>(g, stage, col, m_base, n, cs); break;
-    case EPI_BIAS_DACT: epilogue_act<EPI_BIAS_DACT, LDS_ROW>(g, stage, col, m_base, n, cs); break;
-    case EPI_DACT: epilogue_act<EPI_DACT, LDS_ROW>(g, stage, col, m_base, n, cs); break;
-    default: epilogue_act<EPI_DACT_H, LDS_ROW>(g, stage, col, m_base, n, cs); break;
+    case EPI_STORE: epilogue_vec<EPI_STORE, HF_ACT_NONE, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
+    case EPI_BIAS_ACT: epilogue_act<EPI_BIAS_ACT, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
+    case EPI_BIAS_DACT: epilogue_act<EPI_BIAS_DACT, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
+    case EPI_DACT: epilogue_act<EPI_DACT, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
+    default: epilogue_act<EPI_DACT_H, LDS_ROW>(g, stage, col, m_base, n, cs, kz, row_first, row_step); break;
   }
 }
 
