@@ -22,7 +22,7 @@ def trace(M, N, K):
     ctas = 2 * (-(-M // 256)) * (-(-N // 256))
     t = t[:ctas].double()
     t0 = t[:, 0].min()
-    print(f"M={M} N={N} K={K}: {ctas} CTAs, HF_TC2_BK={os.environ.get('HF_TC2_BK', 'auto')}, event time {e0.elapsed_time(e1)*1e3:.1f} us")
+    print(f"M={M} N={N} K={K}: {ctas} CTAs, HF_TC2_PERSIST={os.environ.get('HF_TC2_PERSIST', '1')}, event time {e0.elapsed_time(e1)*1e3:.1f} us")
     for i, nm in enumerate(NAMES):
         col = t[:, i]; col = col[col > 0]
         if len(col) == 0: continue
