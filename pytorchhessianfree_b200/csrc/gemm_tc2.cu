@@ -627,13 +627,13 @@ static int launch_persistent(const Tc2Maps& maps, const Tc2Args& p, const Tc2Til
 // of tile i runs, the main loop of tile i+1 crawls (both live on shared-memory bandwidth: the MMAs read ~90 B/cycle of
 // operands, the epilogue stages 256 KB per tile through it), so with two tiles per pair the overlap buys less than
 // the narrower passes cost.  HF_TC2P_BK = 16 selects a six-stage / 16-wide ring (slower everywhere measured).
-static int tc2_persist_mode() {
-  static const int mode = getenv("HF_TC2_PERSIST") ? atoi(getenv("HF_TC2_PERSIST")) : 1;
-  return mode;
+static int tc2_persist_mode() {  // read per launch (tests switch it in-process); a getenv is noise next to a launch
+  const char* e = getenv("HF_TC2_PERSIST");
+  return e ? atoi(e) : 1;
 }
 static int tc2p_block_k() {
-  static const int bk = getenv("HF_TC2P_BK") ? atoi(getenv("HF_TC2P_BK")) : 32;
-  return bk == 16 ? 16 : 32;
+  const char* e = getenv("HF_TC2P_BK");
+  return e && atoi(e) == 16 ? 16 : 32;
 }
 
 int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t stream) {
@@ -648,7 +648,11 @@ int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t stream) {
   tl.tiles_m = (g.M + P2_TILE - 1) / P2_TILE, tl.tiles_n = (g.N + P2_TILE - 1) / P2_TILE;
   tl.n_tiles = tl.tiles_m * tl.tiles_n * g.split_k;
   const int hw_pairs = std::max(1, sm_count() / 2);
-  const bool persistent = tc2_persist_mode() == 2 || (tc2_persist_mode() == 1 && tl.n_tiles >= 4 * hw_pairs);
+  // (a short main loop cannot hide the persistent kernel's four-warp, 32-column-pass epilogue: such launches are
+  // epilogue-bound and the one-tile kernel's eight epilogue warps do better)
+  const int kb_per_tile = (g.k_per_split + 31) / 32 * g.n_pairs;
+  const int mode = tc2_persist_mode();
+  const bool persistent = mode == 2 || (mode == 1 && tl.n_tiles >= 4 * hw_pairs && kb_per_tile >= 16);
   const int bk = persistent ? tc2p_block_k() : 32;
   Tc2Maps maps;
   for (int s = 0; s < 2; ++s) {

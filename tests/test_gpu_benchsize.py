@@ -117,3 +117,30 @@ def test_martens_stop_iteration_is_pinned(seed):
     m_ref = torch.stack(ms).double()
     m_dev = torch.stack([m.cpu() for m in ms_d]).double()
     assert torch.allclose(m_dev, m_ref, rtol=1e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("cfg", list(BENCH_CFGS))
+def test_persistent_pair_kernel_through_the_fused_epilogues(cfg, monkeypatch):
+    """HF_TC2_PERSIST=2 sends every pair-engine contraction of a linearisation and of the products through the persistent
+    kernel (double-buffered TMEM accumulator, 32-column epilogue passes, its own column-sum reduction): bias +
+    activation, derivative, second-order term, operand images and bias column sums all come out of its epilogue.  Same
+    bar as the default kernels: the samples of the unmodified reference stored with the fixture."""
+    import copy
+
+    monkeypatch.setenv("HF_TC2_PERSIST", "2")
+    model, loss_fn, x, t, v = benchsize_problem(cfg, 0)
+    gold = next(c for c in BS["cases"] if c["cfg"] == cfg and c["seed"] == 0)
+    idx = torch.arange(0, v.numel(), BS["stride"])
+    got = {}
+    prob, _ = device_problem(copy.deepcopy(model), loss_fn, x, t, "ggn")
+    loss = float(prob.linearize().item())
+    got["grad"], got["Gv"], got["ef"] = prob.gradient(), prob.mvp(v.to(DEV)), prob.fisher_diag()
+    del prob
+    prob, _ = device_problem(copy.deepcopy(model), loss_fn, x, t, "hessian")
+    prob.linearize(), prob.gradient()
+    got["Hv"] = prob.mvp(v.to(DEV))
+    assert abs(loss - float(gold["loss"])) <= 1e-5 * abs(float(gold["loss"]))
+    for k in ("grad", "Gv", "Hv", "ef"):
+        s_max, s_l2 = errs(got[k].cpu()[idx], gold[k])
+        n_rel = abs(float(got[k].double().norm()) - gold[f"{k}_norm"]) / gold[f"{k}_norm"]
+        assert s_l2 < RTOL and n_rel < RTOL, f"{k}: ref-sample max {s_max:.1e} l2 {s_l2:.1e}, norm {n_rel:.1e}"

@@ -66,9 +66,18 @@ def test_single_pair(engine, shape, layout):
     assert err < TOL[engine] * max(1.0, (K / 512) ** 0.5), f"rel err {err:.2e}"  # FP32 accumulation grows ~sqrt(K)
 
 
-@pytest.mark.parametrize("shape", SHAPES2)
+# the persistent pair kernel takes launches of >= 4 waves of 256x256 tiles by itself (the last two shapes: 314 and 320
+# tiles on 74 pairs, ragged edges, 17 and 19 k-blocks); HF_TC2_PERSIST=2 sends every shape through it,
+# HF_TC2P_BK=16 through its six-stage ring
+SHAPES2P = SHAPES2 + [(40000, 512, 520), (20300, 1000, 600)]
+
+
+@pytest.mark.parametrize("persist", ["1", "2", "2/16", "0"])
+@pytest.mark.parametrize("shape", SHAPES2P)
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_pair_engine_shapes(shape, layout):
+def test_pair_engine_shapes(shape, layout, persist, monkeypatch):
+    monkeypatch.setenv("HF_TC2_PERSIST", persist.split("/")[0])
+    monkeypatch.setenv("HF_TC2P_BK", persist.split("/")[1] if "/" in persist else "32")
     M, N, K = shape
     g = torch.Generator(device=DEV).manual_seed(M * 5 + N * 11 + K)
     a = torch.randn(M, K, device=DEV, generator=g)
