@@ -28,6 +28,8 @@ class NativeProblem:
         self.lib = _lib.load()
         self.device = theta.device
         hess = curvature_opt == "hessian"
+        # Chunk products in flight at a time (see _local_products); HF_CHUNK_LANES=1 runs them one after the other.
+        self.chunk_lanes = max(1, int(os.environ.get("HF_CHUNK_LANES", "2"))) if theta.is_cuda else 1
         self.mvp_lins: List[Linearization] = [net.linearize(x, t, hessian=hess) for x, t in mvp_data]
         self.grad_lins = self.mvp_lins if grad_data is None else [net.linearize(x, t) for x, t in grad_data]
         # candidate losses (line search, backtracking, LM ratio) run on their own loss-only linearisations: two
@@ -51,6 +53,7 @@ class NativeProblem:
         # losses: once per step) stays on NCCL.
         self._symm = SymmetricVector.try_create(theta.numel(), self.device, group) if theta.is_cuda else None
         self._side = None
+        self._lanes = []  # (stream, buffer) of lanes 1, 2, ...; lane 0 is the launching stream and `out`
 
     def out_buffer(self):
         """Where the solver should let :meth:`matvec` write its products so that their all-reduce can run through the
@@ -123,13 +126,7 @@ class NativeProblem:
             symm.all_reduce_(0, cut, skip_ptr)
             return
         if nvls:
-            if not self.mvp_lins:
-                out.zero_()
-            for i, lin in enumerate(self.mvp_lins):
-                if self.curvature_opt == "hessian":
-                    lin.hessian(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)
-                else:
-                    lin.ggn(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)
+            self._local_products(v, out, skip_ptr)
             self._symm.all_reduce_(0, self._symm.numel, skip_ptr)
             return
         if self.overlap_allreduce and self.group is not None and len(self.mvp_lins) == 1 and self._split_at > 0:
@@ -143,14 +140,50 @@ class NativeProblem:
             upper.wait()
             first.wait()
             return
-        if not self.mvp_lins:
-            out.zero_()  # empty shard: contribute nothing to the sum over ranks
-        for i, lin in enumerate(self.mvp_lins):
-            if self.curvature_opt == "hessian":
-                lin.hessian(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)
-            else:
-                lin.ggn(self.theta, v, out, accumulate=i > 0, skip_ptr=skip_ptr)
+        self._local_products(v, out, skip_ptr)
         _all_reduce(out, self.group)
+
+    def _local_products(self, v, out, skip_ptr):
+        """``out`` = sum over this rank's chunks of the chunk's curvature product.
+
+        With two chunks or more, ``chunk_lanes`` (2) products are in flight: lane 0 accumulates its chunks into ``out``
+        on the launching stream, every other lane into a buffer of its own on its own stream, and the lanes are added
+        in a fixed order (deterministic).
+        The contractions of a 7 500-row chunk are 120 pair tiles on 74 SM pairs: the second wave of every launch leaves
+        28 pairs idle, and the chain of one product is sequential layer by layer -- the other lane's launches fill them."""
+        lins = self.mvp_lins
+        if not lins:
+            out.zero_()  # empty shard: contribute nothing to the sum over ranks
+            return
+        hess = self.curvature_opt == "hessian"
+
+        def product(lin, dst, accumulate):
+            if hess:
+                lin.hessian(self.theta, v, dst, accumulate=accumulate, skip_ptr=skip_ptr)
+            else:
+                lin.ggn(self.theta, v, dst, accumulate=accumulate, skip_ptr=skip_ptr)
+
+        n_lanes = min(self.chunk_lanes, len(lins))
+        if n_lanes < 2:
+            for i, lin in enumerate(lins):
+                product(lin, out, i > 0)
+            return
+        main = torch.cuda.current_stream()
+        while len(self._lanes) < n_lanes - 1:
+            self._lanes.append((torch.cuda.Stream(), torch.empty_like(self.theta)))
+        for stream, _ in self._lanes[:n_lanes - 1]:
+            stream.wait_stream(main)  # the direction is ready; the lane's buffer is no longer being read
+        for i, lin in enumerate(lins):
+            lane = i % n_lanes
+            if lane == 0:
+                product(lin, out, i >= n_lanes)
+            else:
+                stream, buf = self._lanes[lane - 1]
+                with torch.cuda.stream(stream):
+                    product(lin, buf, i >= n_lanes)
+        for stream, buf in self._lanes[:n_lanes - 1]:
+            main.wait_stream(stream)
+            out.add_(buf)  # fixed order; (after the solver's skip flag is up nothing reads `out` any more)
 
     def mvp(self, v):
         """Tensor-in / tensor-out form of :meth:`matvec` (the reference's ``mvp`` plug-in signature)."""
