@@ -499,7 +499,11 @@ def contraction_roofline(lib, dev, pk, engine, M, N, K, what, flush):
     f = 2.0 * M * N * K
     tf = f / (t * 1e-3) / 1e12
     return dict(bound="tensor", achieved=tf, peak=pk["tf"], unit="TFLOP/s", frac=tf / pk["tf"],
-                traffic=None,  # dram bytes per launch come from ncu --set full: profiles/r2_summary.md
+                # dram__bytes_read.sum + dram__bytes_write.sum of exactly this launch (L2 flushed before it) from one
+                # `ncu --set full` capture (tools/roofline_kernel.py, profiles/r2_summary.md): 62.1 MB read + 8.3 MB written
+                # (most of the 30 MB of C is still in the L2 when the kernel ends) against 83.5 MB of operand forms + C
+                traffic=70.45e6 if (eng == 3 and (M, N, K) == (7500, 1000, 784)) else None,
+                traffic_source="ncu --set full, gpurun_out/prof_r2_roofline.ncu-rep, summarised in profiles/r2_summary.md",
                 peak_source=pk["src"], kernel=f"{kernel}: contraction {M}x{N}x{K} ({what})", us_per_launch=1e3 * t,
                 flops_per_launch=f,
                 note="split precision (TF32 main term + two BF16 correction terms = 4 bf16-MMA equivalents per product), "
