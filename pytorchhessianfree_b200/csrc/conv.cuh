@@ -179,6 +179,117 @@ __global__ void __launch_bounds__(256) unpool_kernel(const float* __restrict__ c
   }
 }
 
+// ---- empirical-Fisher diagonal of a convolution -----------------------------------------------------------
+// For a layer applied at S positions per sample the per-sample gradient is a SUM over positions, and the square sits
+// outside it:   F[co, k] = sum_n ( sum_pos cot[(n, pos), co] * U[(n, pos), k] )^2,   F_b[co] = sum_n ( sum_pos cot )^2
+// -- not the (d^2)^T (a^2) contraction of the fully connected layers.  One CTA owns a 64 x 64 tile of (co, k) and a
+// group of samples: per sample a [64 x S] x [S x 64] product in registers (4 x 4 per thread, 16 positions per shared
+// stage), squared and added to the CTA's running tile; the groups' partial tiles go to part[group][co][k] and
+// reduce_partials2_kernel sums them in a fixed order (deterministic; it also re-orders tap-major k into PyTorch's
+// channel-major weight layout).  FP32 on the CUDA cores: once per optimizer step, ~2 curvature products' worth.
+__global__ void __launch_bounds__(256) conv_fisher_w_kernel(const float* __restrict__ cot, int ld_c, const float* __restrict__ U, int ld_u,
+                                                            int64_t n_samples, int S, int M, int K, int samples_per_group,
+                                                            float* __restrict__ part, const int32_t* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ __align__(16) float sc[16][64];
+  __shared__ __align__(16) float su[16][64];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int co0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  const int64_t s_begin = (int64_t)blockIdx.z * samples_per_group;
+  const int64_t s_end = min(n_samples, s_begin + samples_per_group);
+  const int lr = t >> 4, lc = (t & 15) * 4;  // this thread's slot of a 16 x 64 stage
+  float sq[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sq[i][j] = 0.f;
+  for (int64_t smp = s_begin; smp < s_end; ++smp) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int p0 = 0; p0 < S; p0 += 16) {
+      const int pos = p0 + lr;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (pos < S) {
+        const int64_t row = smp * S + pos;
+        const float* pc = cot + row * ld_c + co0 + lc;
+        const float* pu = U + row * ld_u + k0 + lc;
+        if (co0 + lc + 4 <= M) {
+          a = *reinterpret_cast<const float4*>(pc);
+        } else {
+          if (co0 + lc + 0 < M) a.x = pc[0];
+          if (co0 + lc + 1 < M) a.y = pc[1];
+          if (co0 + lc + 2 < M) a.z = pc[2];
+        }
+        if (k0 + lc + 4 <= K) {
+          b = *reinterpret_cast<const float4*>(pu);
+        } else {
+          if (k0 + lc + 0 < K) b.x = pu[0];
+          if (k0 + lc + 1 < K) b.y = pu[1];
+          if (k0 + lc + 2 < K) b.z = pu[2];
+        }
+      }
+      *reinterpret_cast<float4*>(&sc[lr][lc]) = a;
+      *reinterpret_cast<float4*>(&su[lr][lc]) = b;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        const float4 x = *reinterpret_cast<const float4*>(&sc[kk][ty * 4]);
+        const float4 y = *reinterpret_cast<const float4*>(&su[kk][tx * 4]);
+        const float xv[4] = {x.x, x.y, x.z, x.w}, yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sq[i][j] = fmaf(acc[i][j], acc[i][j], sq[i][j]);
+  }
+  float* dst = part + (int64_t)blockIdx.z * M * K;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) dst[(int64_t)co * K + k] = sq[i][j];
+    }
+  }
+}
+
+// part[group][co] = sum over the group's samples of ( sum over the sample's positions of cot[(n, pos), co] )^2
+__global__ void __launch_bounds__(256) conv_fisher_b_kernel(const float* __restrict__ cot, int ld_c, int64_t n_samples, int S, int M,
+                                                            int samples_per_group, float* __restrict__ part, const int32_t* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t s_begin = (int64_t)blockIdx.y * samples_per_group;
+  const int64_t s_end = min(n_samples, s_begin + samples_per_group);
+  float total = 0.f;
+  for (int64_t smp = s_begin; smp < s_end; ++smp) {
+    float s = 0.f;
+    if (c < M)
+      for (int pos = threadIdx.y; pos < S; pos += 8) s += cot[(smp * S + pos) * ld_c + c];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+      float tsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tsum += sm[i][threadIdx.x];
+      total = fmaf(tsum, tsum, total);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.y == 0 && c < M) part[(int64_t)blockIdx.y * M + c] = total;
+}
+
 inline unsigned conv_blocks(int64_t total) {
   int64_t b = (total + 255) / 256;
   const int64_t cap = 16 * (int64_t)sm_count();

@@ -519,6 +519,44 @@ static int layer_gradient(hf_lin* lin, const Layer& L, int64_t rows, int M, int 
   return HF_OK;
 }
 
+// Empirical-Fisher slices of a layer applied at S > 1 positions per sample (convolutions): conv.cuh, conv_fisher_*.
+// cot = per-sample output cotangents [N*S, M], U = the layer's (unfolded) input [N*S, K].
+static int conv_fisher_gradient(hf_lin* lin, const Layer& L, int M, int K, const float* cot, int ld_c, const float* U, int ld_u,
+                                float* out_w, float* colbuf, float* out_b, float scale, int accumulate, const int32_t* skip,
+                                cudaStream_t stream) {
+  const int S = L.s_out;
+  const int64_t n = lin->N;
+  int groups_w = 0, groups_b = 0;
+  if (out_w) {
+    const int64_t tiles = (int64_t)((M + 63) / 64) * ((K + 63) / 64);
+    int64_t want = std::max<int64_t>(1, (2 * sm_count() + tiles - 1) / tiles);          // ~two CTAs per SM
+    want = std::min<int64_t>(want, (int64_t)(lin->partial_floats / ((size_t)M * K)));   // what the split-K scratch holds
+    want = std::max<int64_t>(1, std::min<int64_t>(want, n));
+    const int per = (int)((n + want - 1) / want);
+    groups_w = (int)((n + per - 1) / per);
+    HF_REQUIRE((size_t)groups_w * M * K <= lin->partial_floats, HF_ERR_WORKSPACE, "Fisher scratch too small");
+    conv_fisher_w_kernel<<<dim3((K + 63) / 64, (M + 63) / 64, groups_w), 256, 0, stream>>>(cot, ld_c, U, ld_u, n, S, M, K, per, lin->partial,
+                                                                                           skip);
+    HF_LAUNCH_CHECK();
+  }
+  if (out_b) {
+    int64_t want = std::min<int64_t>(std::min<int64_t>((int64_t)lin->col_rows, n), std::max<int64_t>(1, 4 * sm_count() / ((M + 31) / 32)));
+    const int per = (int)((n + want - 1) / want);
+    groups_b = (int)((n + per - 1) / per);
+    conv_fisher_b_kernel<<<dim3((M + 31) / 32, groups_b), dim3(32, 8), 0, stream>>>(cot, ld_c, n, S, M, per, colbuf, skip);
+    HF_LAUNCH_CHECK();
+  }
+  const int64_t count_w = out_w ? (int64_t)M * K : 0, count_b = out_b ? M : 0;
+  if (count_w + count_b == 0) return HF_OK;
+  int64_t blocks = (count_w / 4 + count_b + 255) / 256 + 1;
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  const int taps = L.unfold ? L.geom.kh * L.geom.kw : 0;
+  reduce_partials2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lin->partial, groups_w, count_w, out_w, colbuf, groups_b, count_b, out_b,
+                                                               scale, accumulate, skip, L.geom.cin, taps);
+  HF_LAUNCH_CHECK();
+  return HF_OK;
+}
+
 static float loss_scale(const hf_net* net, int64_t n_total) {
   if (net->reduction == HF_RED_SUM) return 1.f;
   if (net->loss == HF_LOSS_SOFTMAX_CE) return (float)(1.0 / (double)n_total);
@@ -792,9 +830,14 @@ static int backward_sweep(hf_lin* lin, const float* theta, const float* v, const
       // it runs there (own split-K scratch) while the side stream finishes the upper layers' reductions.
       const bool on_main = fork && l == net->first_trainable && lin->partial_main != nullptr;
       if (fork && !on_main) HF_CUDA(cudaStreamWaitEvent(gstream, lin->ev[l], 0));
-      int rc = layer_gradient(lin, L, rows, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
-                              cur_col_tiles, lin->colbuf[l], has_b ? out + L.b_off : nullptr, scale, accumulate, skip,
-                              on_main ? stream : gstream, on_main);
+      int rc;
+      if (square && L.s_out > 1)  // a layer applied at several positions per sample: the square sits outside their sum
+        rc = conv_fisher_gradient(lin, L, L.out, L.in, cur, ld_out, a_in, ld_in, L.w_off >= 0 ? out + L.w_off : nullptr, lin->colbuf[l],
+                                  has_b ? out + L.b_off : nullptr, scale, accumulate, skip, gstream);
+      else
+        rc = layer_gradient(lin, L, rows, L.out, L.in, np, A, B, square, L.w_off >= 0 ? out + L.w_off : nullptr, cur, ld_out,
+                            cur_col_tiles, lin->colbuf[l], has_b ? out + L.b_off : nullptr, scale, accumulate, skip,
+                            on_main ? stream : gstream, on_main);
       if (rc) return rc;
     }
     cur_col_tiles = 0;
@@ -1425,9 +1468,8 @@ int hf_hessian_matvec(hf_lin_t* lin, const float* d_theta, const float* d_v, flo
 int hf_fisher_diag(hf_lin_t* lin, const float* d_theta, float* d_out, int32_t accumulate, void* stream) {
   int rc = check_ready(lin, "hf_fisher_diag", false);
   if (rc) return rc;
-  // for a convolution the square sits outside the sum over positions: (d^2)^T (a^2) is NOT the diagonal (SURVEY.md
-  // section 7, hard part 7); per-sample weight-gradient tiles are the next step
-  HF_REQUIRE(!lin->net->has_conv, HF_ERR_UNSUPPORTED, "the empirical-Fisher diagonal of convolutional nets is not lowered yet");
+  // (for a convolution the square sits outside the sum over positions: (d^2)^T (a^2) is NOT the diagonal, SURVEY.md
+  // section 7, hard part 7; those layers go through conv_fisher_gradient)
   HF_REQUIRE(d_out, HF_ERR_INVALID, "hf_fisher_diag: null output");
   return backward_sweep(lin, d_theta, nullptr, lin->deltaL, d_out, accumulate, BACK_FISHER, nullptr,
                         (cudaStream_t)stream);

@@ -1,7 +1,8 @@
 """GPU: the first convolutional slice (reference examples/run_allcnnc_cifar100_deepobs.py,
 eval mode): Conv2d / ReLU / global average pool / Linear nets lowered to the layer program -- loss, gradient and GGN
 products against the CPU oracle (autograd on the same module), chunked == full batch, optimizer steps against the
-oracle's, Hessian products, and a loud refusal for what is not lowered yet (the Fisher diagonal of conv nets)."""
+oracle's, Hessian products, the empirical-Fisher diagonal (per-sample gradients summed over positions BEFORE the
+square) against a per-sample autograd loop, and a loud refusal for what is not lowered."""
 import copy
 import warnings
 
@@ -194,12 +195,67 @@ def test_step_and_static_products_through_the_autograd_graph():
     assert opt.state["num_cg_iters"] == orc.log["num_cg_iters"]
 
 
+def test_allcnnc_fisher_diagonal_at_batch_12():
+    """The preconditioner of the reference's All-CNN-C example: empirical-Fisher diagonal of all nine convolutions
+    (3x3 with and without stride, 1x1, K from 27 to 1 728, up to 1 024 positions per sample) against the per-sample loop."""
+    torch.manual_seed(0)
+    model = allcnnc()
+    loss_fn = nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(11)
+    x, t = torch.rand(12, 3, 32, 32, generator=g), torch.randint(0, 100, (12,), generator=g)
+    want = per_sample_ef(model, loss_fn, x, t, "mean")
+    prob = device_problem(model, loss_fn, [(x[:5], t[:5]), (x[5:], t[5:])], "tc")
+    prob.linearize()
+    e = errs(prob.fisher_diag(), want)
+    print(f"\nAll-CNN-C N=12 Fisher diagonal: max {e[0]:.1e} l2 {e[1]:.1e}")
+    assert max(e) < 1e-4
+
+
+def per_sample_ef(model, loss_fn, x, t, reduction):
+    """sum_n g_n^2 ("sum") or (1/N) sum_n g_n^2 ("mean") with g_n the gradient of sample n's own loss: the reference's
+    autograd variant (preconditioners.py:63-105) with the batch dimension kept for the convolutions."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    acc = torch.zeros(sum(p.numel() for p in params), dtype=torch.float64)
+    for i in range(x.shape[0]):
+        li = loss_fn(model(x[i:i + 1]), t[i:i + 1])
+        acc += O.flatten(torch.autograd.grad(li, params)).double() ** 2
+    return acc / x.shape[0] if reduction == "mean" else acc
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+@pytest.mark.parametrize("n", [1, 5, 70])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_conv_fisher_diagonal_matches_per_sample_loop(name, n, engine):
+    model, loss_fn, x, t = make_case(name, n, 1)
+    want = per_sample_ef(model, loss_fn, x, t, "mean")
+    prob = device_problem(model, loss_fn, [(x, t)], engine)
+    prob.linearize()
+    e = errs(prob.fisher_diag(), want)
+    assert max(e) < 1e-4, f"one chunk: max {e[0]:.1e} l2 {e[1]:.1e}"
+    if n >= 5:  # chunked == full (the chunk sum is exact for a sum over samples)
+        parts = device_problem(model, loss_fn, [(x[:2], t[:2]), (x[2:], t[2:])], engine)
+        parts.linearize()
+        e = errs(parts.fisher_diag(), want)
+        assert max(e) < 1e-4, f"two chunks: max {e[0]:.1e} l2 {e[1]:.1e}"
+
+
+def test_conv_preconditioner_through_the_public_api():
+    """get_preconditioner + acc_step on a conv net (the call sequence of the reference's DeepOBS example)."""
+    model, loss_fn, x, t = make_case("small_cnn_ce", 24, 2)
+    m = copy.deepcopy(model).to(DEV)
+    opt = HessianFree(m.parameters(), cg_max_iter=20)
+    xd, td = x.to(DEV), t.to(DEV)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        M = opt.get_preconditioner(m, loss_fn, xd, td, "mean")
+        before = float(loss_fn(m(xd), td))
+        opt.acc_step(m, loss_fn, [(xd, td)], M_func=M)
+        after = float(loss_fn(m(xd), td))
+    assert after < before
+
+
 def test_unlowered_conv_features_are_refused_loudly():
     model, loss_fn, x, t = make_case("small_cnn_ce", 4, 0)
-    m = copy.deepcopy(model).to(DEV)
-    opt = HessianFree(m.parameters())
-    with pytest.raises(NotImplementedError, match="Fisher"):
-        opt.get_preconditioner(m, loss_fn, x.to(DEV), t.to(DEV), "mean")
     bad = nn.Sequential(nn.Conv2d(3, 4, 3, groups=1, dilation=2), nn.AdaptiveAvgPool2d(1), nn.Flatten())
     with pytest.raises(NotImplementedError):
         lower_module(bad, loss_fn, list(bad.parameters()), input_shape=(3, 8, 8))

@@ -27,5 +27,8 @@ for N in (64, 256, 1024):
         ms = e0.elapsed_time(e1) / reps
         flops = 2.0 * N * (4 * S - 2 * m1)
         ws = sum(l.workspace.numel() for l in prob.mvp_lins) / 2**30
-        print(f"All-CNN-C N={N} engine={engine}: GGN product {ms:.2f} ms = {flops/ms/1e9:.1f} TFLOP/s algorithmic; linearise {t_lin:.1f} ms; workspace {ws:.1f} GiB", flush=True)
+        prob.fisher_diag(); torch.cuda.synchronize()
+        e0.record(); prob.fisher_diag(); e1.record(); torch.cuda.synchronize()
+        print(f"All-CNN-C N={N} engine={engine}: GGN product {ms:.2f} ms = {flops/ms/1e9:.1f} TFLOP/s algorithmic; linearise {t_lin:.1f} ms; "
+              f"Fisher diagonal {e0.elapsed_time(e1):.1f} ms; workspace {ws:.1f} GiB", flush=True)
         del prob
