@@ -50,6 +50,10 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         q.put((rank,) + _train(rank, world, dist.group.WORLD))
+    except Exception as e:  # noqa: BLE001 -- report instead of leaving the parent to time out
+        import traceback
+
+        q.put((rank, "error", f"{e!r}\n{traceback.format_exc()}"))
     finally:
         dist.destroy_process_group()
 
@@ -66,7 +70,9 @@ def test_two_rank_acc_step_equals_single_process(exchange, monkeypatch):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    got = sorted([q.get(timeout=150) for _ in procs], key=lambda r: r[0])
+    for r in got:
+        assert r[1] != "error", r[2]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
