@@ -9,9 +9,10 @@
 //   all-gather         multimem.st writes the sum to the same offset of ALL ranks' buffers -- one store, 8 copies
 //   barrier            every slice has landed everywhere
 // Each element is summed exactly once, by its owner, and the same bits are broadcast to everybody: the replicas stay
-// bit-identical (which the CG replicas rely on: no scalar collectives).  Per rank and direction only 1/W of the vector
-// crosses its own link twice; the 11.3 MB vector of the autoencoder config takes ~25 us on 8 GPUs where ncclAllReduce
-// (latency-bound at this size) takes 85 us (profiles/r2_summary.md).
+// bit-identical (which the CG replicas rely on: no scalar collectives).  Every rank ships (W-1)/W of its vector out
+// (serving the owners' reductions) and takes (W-1)/W of the result in; the 11.3 MB vector of the autoencoder config
+// takes 41-43 us on 8 GPUs (12.7 us of it launch + the two rendezvous) where ncclAllReduce, latency-bound at this
+// size, takes 85 us (tools/scale_probe.py, profiles/r2_summary.md).
 #include "common.cuh"
 
 namespace hf {

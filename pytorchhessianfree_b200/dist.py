@@ -57,6 +57,13 @@ def global_count(n_local, group=None, device=None):
 NVLS_DEFAULT = True
 
 
+def padded_range(begin, end, quantum, limit):
+    """[begin, end) widened to multiples of ``quantum`` (= 4 floats x world: every rank reduces a whole number of 16-byte
+    groups), clipped to ``limit`` (itself a multiple of ``quantum``).  Two ranges that share an end point which is a
+    multiple of ``quantum`` stay disjoint -- what the sliced (overlapped) form of the exchange relies on."""
+    return begin // quantum * quantum, min(limit, (end + quantum - 1) // quantum * quantum)
+
+
 class SymmetricVector:
     """A flat FP32 vector in symmetric memory (same buffer on every rank of ``group``, peer-mapped, behind one NVSwitch
     multicast address) with an in-place all-reduce(sum) through the switch: ``hf_allreduce_multimem`` (csrc/collective.cu,
@@ -101,7 +108,7 @@ class SymmetricVector:
         want = force or os.environ.get("HF_NVLS", "1" if NVLS_DEFAULT else "0") == "1"
         if group is None or not want or dist.get_backend(group) != "nccl":
             return None
-        key = (id(group), int(numel), str(device))
+        key = (getattr(group, "group_name", id(group)), int(numel), str(device))
         if key not in SymmetricVector._cache:
             try:
                 SymmetricVector._cache[key] = SymmetricVector(numel, device, group)
@@ -111,8 +118,7 @@ class SymmetricVector:
 
     def padded_range(self, begin, end):
         """[begin, end) of the vector widened to the collective's granularity (the padding holds zeros on every rank)."""
-        q = self.quantum
-        return begin // q * q, min(self.buf.numel(), (end + q - 1) // q * q)
+        return padded_range(begin, end, self.quantum, self.buf.numel())
 
     def all_reduce_(self, begin=0, end=None, skip_ptr=None, stream=None):
         """In-place sum over the ranks of elements [begin, end) (widened with ``padded_range``), on ``stream``."""

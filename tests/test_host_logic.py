@@ -200,3 +200,23 @@ def test_graph_and_module_lowering_agree_on_a_conv_net():
     o = pooled(x)
     g2 = lower_graph(nn.MSELoss()(o, torch.rand(2, 8)), o, list(pooled.parameters()))
     assert [(l.kind, l.act) for l in g2.layers] == [("conv2d", "tanh"), ("avgpool", "none")]
+
+
+def test_exchange_ranges_are_whole_quanta_and_disjoint():
+    """hf_allreduce_multimem wants offset % 4 == 0 and count % (4 * world) == 0; the sliced form of the exchange cuts
+    the vector at a widened end point and must not reduce any element twice."""
+    from pytorchhessianfree_b200.dist import padded_range
+
+    for world in (2, 4, 8):
+        q = 4 * world
+        for numel in (1, q - 1, q, 2837314, 669706):
+            limit = (numel + q - 1) // q * q
+            lo, hi = padded_range(0, numel, q, limit)
+            assert (lo, hi) == (0, limit) and (hi - lo) % q == 0
+            for split in (4, 784000, numel // 3):
+                if not 0 < split < numel:
+                    continue
+                cut = padded_range(0, split, q, limit)[1]
+                first, second = padded_range(0, cut, q, limit), padded_range(cut, numel, q, limit)
+                assert first == (0, cut) and second == (cut, limit)  # disjoint, together the whole padded vector
+                assert cut >= split and cut % q == 0 and cut % 4 == 0
