@@ -170,7 +170,13 @@ def lower_module(model, loss_func, params_list, input_shape=None):
                 _unsupported("an activation that does not directly follow a Linear or Conv2d layer")
             layers[-1].act = _ACT_MODULES[type(m)]
         elif isinstance(m, (nn.Identity, nn.Flatten)):
-            if isinstance(m, nn.Flatten) and layers and not (fmap is not None and fmap[1:] == (1, 1)):
+            if isinstance(m, nn.Flatten) and not layers and fmap is not None and (m.start_dim, m.end_dim) == (1, -1):
+                # image-shaped inputs into a fully connected net (the MNIST MLPs): the samples are vectors of c*h*w
+                # values from here on (native.Linearization flattens the inputs the same way)
+                if fmap[0] * fmap[1] * fmap[2] <= 0:
+                    raise ValueError("empty input feature map")
+                fmap = None
+            elif isinstance(m, nn.Flatten) and layers and not (fmap is not None and fmap[1:] == (1, 1)):
                 _unsupported("Flatten after the first layer (other than of a 1x1 feature map)")
         elif isinstance(m, nn.Dropout):
             if m.training and m.p > 0:

@@ -220,3 +220,19 @@ def test_exchange_ranges_are_whole_quanta_and_disjoint():
                 first, second = padded_range(0, cut, q, limit), padded_range(cut, numel, q, limit)
                 assert first == (0, cut) and second == (cut, limit)  # disjoint, together the whole padded vector
                 assert cut >= split and cut % q == 0 and cut % 4 == 0
+
+
+def test_flatten_in_front_of_a_fully_connected_net_is_lowered():
+    """Image-shaped inputs into an MLP (nn.Flatten first): the layer program starts at the first Linear; a Linear applied
+    to an unflattened feature map (torch would contract the last axis only) stays refused."""
+    import torch.nn as nn
+
+    from pytorchhessianfree_b200.lowering import lower_module
+
+    loss = nn.CrossEntropyLoss()
+    mlp = nn.Sequential(nn.Flatten(), nn.Linear(784, 32), nn.ReLU(), nn.Linear(32, 10))
+    prog = lower_module(mlp, loss, list(mlp.parameters()), input_shape=(1, 28, 28))
+    assert [(l.kind, l.in_features, l.out_features, l.act) for l in prog.layers] == [("linear", 784, 32, "relu"), ("linear", 32, 10, "none")]
+    bare = nn.Sequential(nn.Linear(28, 32), nn.ReLU(), nn.Linear(32, 10))
+    with pytest.raises(NotImplementedError, match="feature map"):
+        lower_module(bare, loss, list(bare.parameters()), input_shape=(1, 28, 28))
