@@ -254,6 +254,31 @@ def test_conv_preconditioner_through_the_public_api():
     assert after < before
 
 
+def test_image_shaped_inputs_into_a_flatten_first_mlp():
+    """nn.Flatten in front of a fully connected net, inputs [n, c, h, w] (the MNIST-MLP pattern): gradient, GGN product
+    and Fisher diagonal against the oracle, and an `acc_step` through the public API."""
+    torch.manual_seed(3)
+    model = nn.Sequential(nn.Flatten(), nn.Linear(3 * 6 * 6, 24), nn.Tanh(), nn.Linear(24, 5))
+    loss_fn = nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(5)
+    x, t = torch.rand(19, 3, 6, 6, generator=g), torch.randint(0, 5, (19,), generator=g)
+    params = list(model.parameters())
+    out = model(x)
+    loss = loss_fn(out, t)
+    v = torch.randn(sum(p.numel() for p in params), generator=g)
+    prob = device_problem(model, loss_fn, [(x, t)], "tc")
+    assert abs(prob.linearize().item() - float(loss)) <= 1e-5 * float(loss)
+    assert max(errs(prob.gradient(), O.flatten(torch.autograd.grad(loss, params, retain_graph=True)))) < 1e-4
+    assert max(errs(prob.mvp(v.to(DEV)), O.Gv(loss, out, params, v))) < 1e-4
+    assert max(errs(prob.fisher_diag(), per_sample_ef(model, loss_fn, x, t, "mean"))) < 1e-4
+    m = copy.deepcopy(model).to(DEV)
+    opt = HessianFree(m.parameters(), cg_max_iter=10)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        opt.acc_step(m, loss_fn, [(x.to(DEV), t.to(DEV))])
+    assert float(loss_fn(m(x.to(DEV)), t.to(DEV))) < float(loss)
+
+
 def test_unlowered_conv_features_are_refused_loudly():
     model, loss_fn, x, t = make_case("small_cnn_ce", 4, 0)
     bad = nn.Sequential(nn.Conv2d(3, 4, 3, groups=1, dilation=2), nn.AdaptiveAvgPool2d(1), nn.Flatten())
