@@ -201,6 +201,42 @@ def gold_benchsize(stride=997):
     print(f"benchsize.pt: {len(cases)} cases")
 
 
+def gold_conv():
+    """The convolutional slice: the small CNNs of tests/test_gpu_conv.py (3x3 'same' / strided / 'valid', 1x1, bias on and
+    off, global average pool, a Linear head; ReLU / tanh / sigmoid; CE / MSE / BCE), the reference's seeds, batch 1 and 6:
+    loss, gradient, `_Gv`, `_Hv` from the unmodified reference + float64 dense `J^T H J v` and `H v` known answers."""
+    from test_gpu_conv import CASES, make_case
+
+    out = []
+    for name in sorted(CASES):
+        for seed in SEEDS:
+            for n in (1, 6):
+                model, loss_fn, x, t = make_case(name, n, seed)
+                params = list(model.parameters())
+                g = torch.Generator().manual_seed(seed + 200)
+                v = torch.randn(sum(p.numel() for p in params), generator=g)
+                outputs = model(x)
+                loss = loss_fn(outputs, t)
+                grad = O.flatten(torch.autograd.grad(loss, params, create_graph=True)).detach()
+                Gv = RefHF._Gv(loss, outputs, params, v)
+                Hv = RefHF._Hv(loss, params, v)
+                same(Gv, O.Gv(loss, outputs, params, v), "conv Gv")
+                same(Hv, O.Hv(loss, params, v), "conv Hv")
+                # independent pin (no R-op recipe): float64 dense J^T H J and the full Hessian of these ~2 000-parameter nets
+                m64 = copy.deepcopy(model).double()
+                t64 = t.double() if t.is_floating_point() else t
+                G = O.explicit_ggn(m64, loss_fn, x.double(), t64)
+                H = O.explicit_hessian(m64, loss_fn, x.double(), t64)
+                Gd, Hd = G @ v.double(), H @ v.double()
+                same(Gd, Gv.double(), "conv dense GGN vs Gv", tol=2e-5)
+                same(Hd, Hv.double(), "conv dense H vs Hv", tol=2e-5)
+                out.append(dict(net=name, seed=seed, n=n, x=x, t=t, v=v,
+                                state={k: w.detach().clone() for k, w in model.state_dict().items()},
+                                loss=loss.detach(), grad=grad, Gv=Gv, Hv=Hv, Gv_dense64=Gd, Hv_dense64=Hd))
+    torch.save(out, os.path.join(HERE, "conv.pt"))
+    print(f"conv.pt: {len(out)} cases")
+
+
 # ---------------------------------------------------------------------------
 def run_ref_steps(name, seed, reduction, curv, n_steps, n, precond, chunks=None, **hf_kw):
     """n_steps of the reference optimizer; the oracle class must land on the same trajectory."""
@@ -349,9 +385,14 @@ if __name__ == "__main__":
         torch.set_num_threads(1)
         gold_resume()
         sys.exit(0)
+    if "conv" in sys.argv:
+        torch.set_num_threads(1)
+        gold_conv()
+        sys.exit(0)
     torch.set_num_threads(1)  # bit-stable reductions while minting
     gold_cg()
     gold_matvec()
     gold_steps()
     gold_resume()
     gold_selection()
+    gold_conv()

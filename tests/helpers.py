@@ -99,3 +99,14 @@ def benchsize_problem(cfg, seed):
     g = torch.Generator().manual_seed(2000 + seed)
     v = torch.randn(sum(p.numel() for p in model.parameters() if p.requires_grad), generator=g)
     return model, loss_fn, x, t, v
+
+
+def conv_fixture_case(c):
+    """Rebuild model, loss and data of one record of tests/golden/conv.pt (minted from the unmodified reference by
+    tests/golden/make_golden.py conv; the architectures live in tests/test_gpu_conv.py)."""
+    from test_gpu_conv import CASES
+
+    build, loss_cls, _, _, _ = CASES[c["net"]]
+    model = build()
+    model.load_state_dict(c["state"])
+    return model, loss_cls(), c["x"], c["t"], c["v"]

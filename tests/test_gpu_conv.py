@@ -11,6 +11,7 @@ import torch
 from torch import nn
 
 import hf_oracle as O
+from helpers import GOLDEN, conv_fixture_case
 
 from pytorchhessianfree_b200 import HessianFree
 from pytorchhessianfree_b200.lowering import lower_module
@@ -97,6 +98,28 @@ def test_conv_products_match_oracle(name, n, engine):
         hprob.linearize(), hprob.gradient()
         e_H = errs(hprob.mvp(v.to(DEV)), want_H)
         assert max(e_H) < 1e-4, f"Hessian product: max {e_H[0]:.1e} l2 {e_H[1]:.1e}"
+
+
+CONV_GOLD = torch.load(f"{GOLDEN}/conv.pt", weights_only=False)
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+@pytest.mark.parametrize("i", range(len(CONV_GOLD)))
+def test_conv_products_match_reference_fixture(i, engine):
+    """Against tests/golden/conv.pt: loss, gradient, `_Gv`, `_Hv` as the UNMODIFIED reference returned them for these
+    nets (the GPU box has no reference), and against the float64 dense `J^T H J v` / `H v` stored with them."""
+    c = CONV_GOLD[i]
+    model, loss_fn, x, t, v = conv_fixture_case(c)
+    prob = device_problem(model, loss_fn, [(x, t)], engine)
+    got_loss = float(prob.linearize().item())
+    assert abs(got_loss - float(c["loss"])) <= 1e-5 * abs(float(c["loss"]))
+    assert max(errs(prob.gradient(), c["grad"])) < 1e-4
+    G = prob.mvp(v.to(DEV))
+    assert max(errs(G, c["Gv"])) < 1e-4 and max(errs(G, c["Gv_dense64"])) < 1e-4
+    hprob = device_problem(model, loss_fn, [(x, t)], engine, curv="hessian")
+    hprob.linearize(), hprob.gradient()
+    H = hprob.mvp(v.to(DEV))
+    assert max(errs(H, c["Hv"])) < 1e-4 and max(errs(H, c["Hv_dense64"])) < 1e-4
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

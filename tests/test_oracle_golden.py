@@ -137,3 +137,25 @@ def test_benchsize_oracle_reproduces_one_fixture():
     idx = torch.arange(0, v.numel(), BS["stride"])
     assert torch.allclose(O.Gv(loss, out, params, v)[idx], c["Gv"], rtol=1e-4, atol=1e-8)
     assert torch.allclose(O.ef_diag_layerwise(model, loss_fn, x, t, "mean")[idx], c["ef"], rtol=1e-4, atol=1e-12)
+
+
+CV = torch.load(f"{GOLDEN}/conv.pt", weights_only=False)
+
+
+@pytest.mark.parametrize("i", range(len(CV)))
+def test_conv_matvec_matches_reference(i):
+    """The oracle on the small CNNs against what the unmodified reference returned for them, and the reference's float32
+    products against float64 dense known answers."""
+    from helpers import conv_fixture_case
+
+    c = CV[i]
+    model, loss_fn, x, t, v = conv_fixture_case(c)
+    params = list(model.parameters())
+    out = model(x)
+    loss = loss_fn(out, t)
+    assert torch.allclose(loss, c["loss"], rtol=1e-6)
+    assert torch.allclose(O.flatten(torch.autograd.grad(loss, params, retain_graph=True)), c["grad"], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(O.Gv(loss, out, params, v), c["Gv"], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(O.Hv(loss, params, v), c["Hv"], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(c["Gv"].double(), c["Gv_dense64"], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(c["Hv"].double(), c["Hv_dense64"], rtol=1e-4, atol=1e-6)
