@@ -29,7 +29,7 @@ class NativeProblem:
         self.device = theta.device
         hess = curvature_opt == "hessian"
         # Chunk products in flight at a time (see _local_products); HF_CHUNK_LANES=1 runs them one after the other.
-        self.chunk_lanes = max(1, int(os.environ.get("HF_CHUNK_LANES", "2"))) if theta.is_cuda else 1
+        self.chunk_lanes = max(1, int(os.environ.get("HF_CHUNK_LANES", "4"))) if theta.is_cuda else 1
         self.mvp_lins: List[Linearization] = [net.linearize(x, t, hessian=hess) for x, t in mvp_data]
         self.grad_lins = self.mvp_lins if grad_data is None else [net.linearize(x, t) for x, t in grad_data]
         # candidate losses (line search, backtracking, LM ratio) run on their own loss-only linearisations: two
@@ -146,7 +146,7 @@ class NativeProblem:
     def _local_products(self, v, out, skip_ptr):
         """``out`` = sum over this rank's chunks of the chunk's curvature product.
 
-        With two chunks or more, ``chunk_lanes`` (2) products are in flight: lane 0 accumulates its chunks into ``out``
+        With two chunks or more, up to ``chunk_lanes`` (4) products are in flight: lane 0 accumulates its chunks into ``out``
         on the launching stream, every other lane into a buffer of its own on its own stream, and the lanes are added
         in a fixed order (deterministic).
         The contractions of a 7 500-row chunk are 120 pair tiles on 74 SM pairs: the second wave of every launch leaves
